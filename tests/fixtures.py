@@ -1,0 +1,40 @@
+"""Shared loaders for the committed golden fixtures (tests/golden; see oracle/make_golden.py)."""
+import os
+
+import numpy as np
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_flags_case():
+    """Return (npz, list of per-pulsar dicts) for tests/golden/ref_flags.npz."""
+    z = np.load(os.path.join(GOLD, "ref_flags.npz"), allow_pickle=False)
+    n = int(z["npsr"])
+    psrs = []
+    for i in range(n):
+        raj, decj = z[f"raj_decj_{i}"]
+        psrs.append(dict(
+            name=str(z[f"name_{i}"]), loc={"RAJ": float(raj), "DECJ": float(decj)},
+            mjd=z[f"mjd_{i}"], err_us=z[f"err_{i}"], flag=[str(s) for s in z[f"flag_{i}"]],
+            backends=[str(s) for s in z[f"backends_{i}"]],
+            efac=z[f"efac_{i}"], l10_equad=z[f"l10_equad_{i}"], l10_ecorr=z[f"l10_ecorr_{i}"],
+            rn_l10A=float(z[f"rn_l10A_{i}"]), rn_gamma=float(z[f"rn_gamma_{i}"])))
+    return z, psrs
+
+
+def load_small_case():
+    from pta_replicator_b200 import partim
+    import glob
+    pars = sorted(glob.glob(os.path.join(GOLD, "partim_small", "par", "*.par")))
+    tims = sorted(glob.glob(os.path.join(GOLD, "partim_small", "tim", "*.tim")))
+    psrs = []
+    for p, t in zip(pars, tims):
+        par = partim.read_par(p)
+        c = partim.read_tim(t)
+        psrs.append(dict(name=par["_name"], loc=par["_loc"], mjd=c["mjd"], err_us=c["err_us"], flags=c["flags"]))
+    return np.load(os.path.join(GOLD, "ref_small.npz")), psrs
+
+
+def rel_rms(a, b):
+    """max|a-b| / rms(b)."""
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / np.sqrt(np.mean(np.square(b))))
