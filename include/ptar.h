@@ -1,0 +1,175 @@
+/* ptar.h -- C ABI of the B200 synthetic-PTA residual generator (libptar_b200.so).
+ *
+ * The reference (bencebecsy/pta_replicator) has no FFI: its boundary is a set of
+ * Python functions.  Each entry point below replaces the arithmetic body of one of
+ * them and is what a binding on the reference side would call (INTEGRATION.md shows
+ * the ctypes stub).  Conventions: plain pointers and sizes, no torch types; every
+ * pointer is a DEVICE pointer unless the name ends in _host; the library never
+ * allocates or frees user memory; all work is enqueued on the given cudaStream_t
+ * (passed as void*); return 0 on success, negative on bad arguments / launch errors
+ * (text from ptar_last_error()).  All floating point is IEEE fp64 unless noted.
+ *
+ * Reference lines replaced (paths relative to /root/reference/pta_replicator/):
+ *   ptar_cholesky_lower    np.linalg.cholesky(ORF)                      red_noise.py:235
+ *   ptar_fourier_basis     create_fourier_design_matrix_red             red_noise.py:36-103
+ *   ptar_gwb_mix           w draws + np.dot(M, w)                       red_noise.py:238-240, :268
+ *   ptar_gwb_synth         sqrt(C) scale, Hermitian pack, ifft, crop    red_noise.py:269-285
+ *   ptar_cgw_delay         add_cgw arithmetic                           deterministic.py:98-163
+ *   ptar_generate          efac/equad draw                              white_noise.py:105-109
+ *                          U @ (ecorr*z)                                white_noise.py:182
+ *                          F @ (sqrt(prior)*z)                          red_noise.py:126-128
+ *                          interp1d(ut, Res)(toas)                      red_noise.py:286-287
+ *                          (+ CGW / deterministic delays)               deterministic.py:160-165
+ *   ptar_philox_normals    np.random.randn (throughput-mode stream)     SURVEY.md 3.6
+ */
+#ifndef PTAR_H
+#define PTAR_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTAR_VERSION 100  /* major*100 + minor */
+
+/* Geometry limits of the fused generator kernel. */
+#define PTAR_TILE_TOAS   1024  /* TOAs per tile (256 threads x 4)            */
+#define PTAR_TILE_EPOCHS 64    /* kernel-epochs per tile                     */
+#define PTAR_TOA_ALIGN   4     /* every pulsar segment starts at a multiple  */
+
+/* ptar_gen_params.flags */
+#define PTAR_F_WHITE    1u   /* efac*sigma*z1 + w2*z2                         */
+#define PTAR_F_ECORR    2u   /* ecorr[epoch] * z[bucket(epoch)]               */
+#define PTAR_F_RED      4u   /* Fourier-basis red noise                       */
+#define PTAR_F_GWB      8u   /* linear interpolation of the GWB time grid     */
+#define PTAR_F_DET      16u  /* precomputed deterministic delay (CGW ...)     */
+#define PTAR_F_WHITE1   32u  /* throughput mode only: one N(0, w1^2+w2^2) draw per TOA
+                                instead of two (identical distribution)       */
+
+/* Philox stream tags ("kind") -- part of the counter, see ptar_philox_normals. */
+#define PTAR_K_WHITE1 1
+#define PTAR_K_WHITE2 2
+#define PTAR_K_ECORR  3
+#define PTAR_K_RED    4
+#define PTAR_K_GWB    5
+
+/* One tile of the packed TOA axis: <=1024 consecutive (time-sorted) TOAs of ONE pulsar
+ * touching <=64 kernel-epochs. */
+typedef struct {
+  int32_t toa_start;   /* index into the packed per-TOA arrays (multiple of 4)          */
+  int32_t n_toa;       /* real TOAs in this tile (<= PTAR_TILE_TOAS)                    */
+  int32_t toa_local0;  /* index of toa_start within its pulsar (Philox counter base)    */
+  int32_t ep_start;    /* first kernel-epoch (global index)                             */
+  int32_t n_ep;        /* kernel-epochs touched (<= PTAR_TILE_EPOCHS)                   */
+  int32_t psr;         /* pulsar index                                                  */
+  int32_t nd;          /* Taylor terms used for red noise inside epochs (1..3)          */
+  int32_t reserved;
+} ptar_tile;
+
+typedef struct {
+  /* geometry */
+  int32_t n_psr;
+  int32_t n_tiles;
+  int32_t J;            /* red-noise basis columns (2 * components); 0 if no red noise  */
+  int32_t npts;         /* GWB grid length; 0 if no GWB                                  */
+  uint32_t flags;       /* PTAR_F_*                                                      */
+  int32_t rn_convention;/* 0: (sin,cos) pairs, absolute t;  1: libstempo (cos,sin)      */
+  const ptar_tile* tiles;
+  /* per-TOA statics, packed axis of length ld_out */
+  const double*   w1;    /* efac*sigma [s]                                               */
+  const double*   w2;    /* efac*equad (t2equad) or equad (tnequad) [s]                  */
+  const double*   dtau;  /* t - t_ref(epoch) [s]                                         */
+  const uint16_t* eloc;  /* kernel-epoch index local to the tile                         */
+  const uint16_t* gidx;  /* GWB grid interval                                            */
+  const double*   gw;    /* interpolation weight in [0,1]                                */
+  const double*   det;   /* deterministic delay [s]                                      */
+  /* per-epoch statics */
+  const double*  ep_ecorr;   /* ecorr of the epoch's bucket [s]                          */
+  const int32_t* ep_bucket;  /* ECORR bucket id within the pulsar                        */
+  const int64_t* psr_bucket_off; /* [n_psr]: offset of each pulsar in the injected zb axis */
+  const double*  Ftile;      /* [n_tiles][J][64]: basis at epoch reference times          */
+  /* per-pulsar red-noise statics */
+  const double* rn_scale;    /* [n_psr][J] sqrt(prior)                                   */
+  const double* rn_omega;    /* [n_psr][J/2] 2*pi*f_k                                    */
+  /* GWB grid for this batch of realizations: G[r][psr][npts] */
+  const double* G;
+  /* injected standard-normal draws (parity mode); all NULL => Philox */
+  const double* z1;   /* [nreal][ld_out]                                                 */
+  const double* z2;   /* [nreal][ld_out]                                                 */
+  const double* zb;   /* [nreal][n_bucket_total]                                         */
+  const double* zrn;  /* [nreal][n_psr][J]                                               */
+  int64_t n_bucket_total;
+  /* RNG (throughput mode) */
+  uint64_t seed;
+  int64_t  real0;     /* global id of realization 0 of this call (multiple of 4)         */
+  /* output: out[r][ld_out] */
+  double* out;
+  int64_t ld_out;
+  int32_t nreal;
+  int32_t rc;         /* realizations per CTA: 16 or 32 (0 = default)                    */
+} ptar_gen_params;
+
+int         ptar_version(void);
+const char* ptar_last_error(void);
+
+/* Lower Cholesky factor of `batch` SPD matrices A[b][n][n] (row-major) -> L (strict upper
+ * part zeroed).  info[b] = 0, or k>0 if the leading minor of order k is not PD.  n <= 1024. */
+int ptar_cholesky_lower(double* L, const double* A, int n, int batch, int* info, void* stream);
+
+/* F[row][2k], F[row][2k+1] = trig(2*pi * tprime[row] * freqs[psr(row)][k]) in the reference's
+ * operation order; convention 0 -> (sin, cos), 1 -> (cos, sin).  out index:
+ * out[row_off[row] + col*col_stride] so the caller chooses row-major or per-tile layouts. */
+int ptar_fourier_basis(double* out, const int64_t* row_off, int64_t col_stride,
+                       const double* tprime, const int32_t* row_psr, const double* freqs,
+                       int K, int convention, int64_t nrows, void* stream);
+
+/* Continuous-wave delay per TOA.  src[16] and psr_par[n_psr][4] = {fplus, fcross, cosMu, pd_sec}
+ * are the scalar pre-factors of deterministic.py:51-105; mode 0 evolve, 1 phase_approx, 2 mono.
+ * out[i] (+)= delay(t[i]) ; t = mjd*86400 - tref. */
+int ptar_cgw_delay(double* out, const double* t, const int32_t* psr_of_toa, const double* psr_par,
+                   const double* src, int mode, int psr_term, int accumulate, int64_t n, void* stream);
+
+/* Zm[r][p][j] = sum_q M[p][q] z[r][q][j].  z is read from zin (parity) or drawn from Philox
+ * (zin == NULL; stream PTAR_K_GWB).  M is n_psr x n_psr lower triangular, row-major. */
+int ptar_gwb_mix(double* Zm, const double* M, const double* zin, int n_psr, int J,
+                 int64_t nreal, uint64_t seed, int64_t real0, void* stream);
+
+/* G[c][n] = sum_j A[n][j] * Zm[c][j],  n < npts, c < ncols (= nreal * n_psr).
+ * lower_tri != 0 promises A[n][j] == 0 for j > n (skips those blocks). */
+int ptar_gwb_synth(double* G, const double* A, int64_t lda, const double* Zm, int npts, int J,
+                   int64_t ncols, int lower_tri, void* stream);
+
+/* The fused generator: out[r][i] = white + ecorr + red + gwb + det for nreal realizations. */
+int ptar_generate(const ptar_gen_params* p, void* stream);
+
+/* Raw throughput-mode normals (fp32 Box-Muller of Philox4x32-10), for tests:
+ * out[k] = normal(kind, psr, realization, idx0 + k), k < n. `lane_is_real` selects which of
+ * the two counter groupings the kernels use (0: white, lanes = 4 consecutive idx;
+ * 1: ecorr/red/gwb, lanes = 4 consecutive realizations). */
+int ptar_philox_normals(float* out, int kind, int psr, int64_t realization, int64_t idx0,
+                        int64_t n, int lane_is_real, uint64_t seed, void* stream);
+
+/* End-to-end job: GWB mix + synth + generate for realizations [real0, real0+nreal), then
+ * (ptar_run_job_to_host) copy the residuals to pinned host memory, chunk by chunk, with the
+ * copy of chunk c overlapping the generation of chunk c+1 on a second stream. */
+typedef struct {
+  ptar_gen_params gen;      /* gen.G / gen.out / gen.nreal / gen.real0 are set per chunk  */
+  const double* M;          /* [n_psr][n_psr] lower Cholesky factor of the ORF            */
+  const double* A;          /* [npts][lda] GWB synthesis matrix                           */
+  int64_t lda;
+  int32_t Jg;               /* columns of A                                               */
+  int32_t lower_tri;
+  double* Zm;               /* scratch [chunk][n_psr][Jg]                                 */
+  double* Gbuf;             /* scratch [chunk][n_psr][npts]                               */
+  const double* gwb_zin;    /* parity mode: [nreal][n_psr][Jg] or NULL                    */
+} ptar_job;
+
+int ptar_run_job(const ptar_job* job, int64_t real0, int32_t nreal, double* out, void* stream);
+int ptar_run_job_to_host(const ptar_job* job, int64_t real0, int64_t nreal, int32_t chunk,
+                         double* out_host, double* dev_buf0, double* dev_buf1, void* stream0, void* stream1);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTAR_H */

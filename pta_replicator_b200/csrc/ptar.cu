@@ -1,0 +1,283 @@
+// libptar_b200.so -- C ABI (include/ptar.h) over the sm_100a kernels.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/ptar.h"
+#include "ptar_generate.cuh"
+#include "ptar_gwb.cuh"
+#include "ptar_rng.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, const char* detail = "") {
+  snprintf(g_err, sizeof(g_err), fmt, detail);
+  return code;
+}
+
+int check_launch(const char* what) {
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return -100;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// red_noise.py:92-101 -- operation order kept: (2*pi * t) * f, then sin / cos.
+__global__ void fourier_basis_kernel(double* __restrict__ out, const int64_t* __restrict__ row_off,
+                                     int64_t col_stride, const double* __restrict__ tprime,
+                                     const int32_t* __restrict__ row_psr, const double* __restrict__ freqs, int K,
+                                     int convention, int64_t nrows) {
+  const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= nrows * K) return;
+  const int64_t row = idx / K;
+  const int k = static_cast<int>(idx % K);
+  const double f = freqs[size_t(row_psr[row]) * K + k];
+  const double arg = __dmul_rn(__dmul_rn(6.283185307179586, tprime[row]), f);
+  double s, c;
+  sincos(arg, &s, &c);
+  double* o = out + row_off[row];
+  o[int64_t(2 * k) * col_stride] = convention ? c : s;
+  o[int64_t(2 * k + 1) * col_stride] = convention ? s : c;
+}
+
+// deterministic.py:98-163.  src = {w0, fac1, fac2, fac3, phase0(orbital), w053, incfac1,
+// incfac2, cos2psi, sin2psi}; psr_par[p] = {fplus, fcross, cosMu, pd_seconds}.
+__global__ void cgw_kernel(double* __restrict__ out, const double* __restrict__ t, const int32_t* __restrict__ psr_of_toa,
+                           const double* __restrict__ psr_par, const double* __restrict__ src, int mode, int psr_term,
+                           int accumulate, int64_t n) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double w0 = src[0], fac1 = src[1], fac2 = src[2], fac3 = src[3], phase0 = src[4], w053 = src[5];
+  const double inc1 = src[6], inc2 = src[7], c2p = src[8], s2p = src[9];
+  const double* pp = psr_par + size_t(psr_of_toa[i]) * 4;
+  const double fplus = pp[0], fcross = pp[1], cosMu = pp[2], pd = pp[3];
+  const double toa = t[i];
+  const double tp = toa - pd * (1 - cosMu);
+  double omega, omega_p, phase, phase_p;
+  if (mode == 0) {
+    omega = w0 * pow(1 - fac1 * toa, -3.0 / 8);
+    omega_p = w0 * pow(1 - fac1 * tp, -3.0 / 8);
+    phase = phase0 + fac2 * (w053 - pow(omega, -5.0 / 3));
+    phase_p = phase0 + fac2 * (w053 - pow(omega_p, -5.0 / 3));
+  } else if (mode == 1) {
+    omega = w0;
+    omega_p = w0 * pow(1 + fac1 * pd * (1 - cosMu), -3.0 / 8);
+    phase = phase0 + omega * toa;
+    phase_p = phase0 + fac2 * (w053 - pow(omega_p, -5.0 / 3)) + omega_p * toa;
+  } else {
+    omega = w0;
+    omega_p = omega;
+    phase = phase0 + omega * toa;
+    phase_p = phase0 + omega * tp;
+  }
+  const double At = sin(2 * phase) * inc1, Bt = cos(2 * phase) * inc2;
+  const double Atp = sin(2 * phase_p) * inc1, Btp = cos(2 * phase_p) * inc2;
+  const double alpha = fac3 / cbrt(omega), alpha_p = fac3 / cbrt(omega_p);
+  const double rplus = alpha * (At * c2p + Bt * s2p), rcross = alpha * (-At * s2p + Bt * c2p);
+  const double rplus_p = alpha_p * (Atp * c2p + Btp * s2p), rcross_p = alpha_p * (-Atp * s2p + Btp * c2p);
+  const double res = psr_term ? fplus * (rplus_p - rplus) + fcross * (rcross_p - rcross)
+                              : -fplus * rplus - fcross * rcross;
+  out[i] = accumulate ? out[i] + res : res;
+}
+
+__global__ void philox_normals_kernel(float* __restrict__ out, int kind, int psr, int64_t realization, int64_t idx0,
+                                      int64_t n, int lane_is_real, uint64_t seed) {
+  const int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int64_t idx = idx0 + k;
+  float z[4];
+  if (lane_is_real) {
+    ptar::normals4(z, static_cast<uint32_t>(idx), kind, psr, static_cast<uint64_t>(realization) >> 2, seed);
+    out[k] = z[realization & 3];
+  } else {
+    ptar::normals4(z, static_cast<uint32_t>(idx >> 2), kind, psr, static_cast<uint64_t>(realization), seed);
+    out[k] = z[idx & 3];
+  }
+}
+
+template <int RC, bool INJECT>
+int launch_gen(const ptar_gen_params& p, cudaStream_t st) {
+  const size_t smem = ptar::gen_smem_bytes(p.J, RC);
+  if (smem > 227 * 1024) return fail(-3, "ptar_generate: J too large for shared memory%s");
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    cudaFuncSetAttribute(ptar::gen_kernel<RC, INJECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  const dim3 grid(p.n_tiles, (p.nreal + RC - 1) / RC);
+  ptar::gen_kernel<RC, INJECT><<<grid, ptar::GEN_THREADS, smem, st>>>(p);
+  return check_launch("ptar_generate");
+}
+
+}  // namespace
+
+extern "C" {
+
+int ptar_version(void) { return PTAR_VERSION; }
+const char* ptar_last_error(void) { return g_err; }
+
+int ptar_cholesky_lower(double* L, const double* A, int n, int batch, int* info, void* stream) {
+  if (!L || !A || n <= 0 || n > 1024 || batch <= 0) return fail(-1, "ptar_cholesky_lower: bad argument%s");
+  ptar::cholesky_kernel<<<batch, 256, 0, static_cast<cudaStream_t>(stream)>>>(L, A, n, info);
+  return check_launch("ptar_cholesky_lower");
+}
+
+int ptar_fourier_basis(double* out, const int64_t* row_off, int64_t col_stride, const double* tprime,
+                       const int32_t* row_psr, const double* freqs, int K, int convention, int64_t nrows,
+                       void* stream) {
+  if (!out || !row_off || !tprime || !row_psr || !freqs || K <= 0 || nrows < 0)
+    return fail(-1, "ptar_fourier_basis: bad argument%s");
+  if (nrows == 0) return 0;
+  const int64_t total = nrows * K;
+  fourier_basis_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      out, row_off, col_stride, tprime, row_psr, freqs, K, convention, nrows);
+  return check_launch("ptar_fourier_basis");
+}
+
+int ptar_cgw_delay(double* out, const double* t, const int32_t* psr_of_toa, const double* psr_par, const double* src,
+                   int mode, int psr_term, int accumulate, int64_t n, void* stream) {
+  if (!out || !t || !psr_of_toa || !psr_par || !src || mode < 0 || mode > 2 || n < 0)
+    return fail(-1, "ptar_cgw_delay: bad argument%s");
+  if (n == 0) return 0;
+  cgw_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      out, t, psr_of_toa, psr_par, src, mode, psr_term, accumulate, n);
+  return check_launch("ptar_cgw_delay");
+}
+
+int ptar_gwb_mix(double* Zm, const double* M, const double* zin, int n_psr, int J, int64_t nreal, uint64_t seed,
+                 int64_t real0, void* stream) {
+  if (!Zm || !M || n_psr <= 0 || J <= 0 || nreal <= 0) return fail(-1, "ptar_gwb_mix: bad argument%s");
+  if (!zin && (real0 & 3)) return fail(-2, "ptar_gwb_mix: real0 must be a multiple of 4%s");
+  const size_t smem = sizeof(double) * size_t(n_psr) * ptar::MIX_JT * 4;
+  if (smem > 227 * 1024) return fail(-3, "ptar_gwb_mix: too many pulsars for shared memory%s");
+  const int nwarps = (n_psr + 3) / 4;
+  const int threads = 32 * (nwarps < 4 ? 4 : (nwarps > 32 ? 32 : nwarps));
+  const dim3 grid((J + ptar::MIX_JT - 1) / ptar::MIX_JT, static_cast<unsigned>((nreal + 3) / 4));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (zin) {
+    cudaFuncSetAttribute(ptar::gwb_mix_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    ptar::gwb_mix_kernel<true><<<grid, threads, smem, st>>>(Zm, M, zin, n_psr, J, nreal, seed, real0);
+  } else {
+    cudaFuncSetAttribute(ptar::gwb_mix_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    ptar::gwb_mix_kernel<false><<<grid, threads, smem, st>>>(Zm, M, zin, n_psr, J, nreal, seed, real0);
+  }
+  return check_launch("ptar_gwb_mix");
+}
+
+int ptar_gwb_synth(double* G, const double* A, int64_t lda, const double* Zm, int npts, int J, int64_t ncols,
+                   int lower_tri, void* stream) {
+  if (!G || !A || !Zm || npts <= 0 || J <= 0 || ncols <= 0) return fail(-1, "ptar_gwb_synth: bad argument%s");
+  if ((J & 3) || (lda & 1) || lda < J) return fail(-2, "ptar_gwb_synth: need J %% 4 == 0 and even lda >= J%s");
+  const dim3 grid((npts + ptar::SY_BM - 1) / ptar::SY_BM, static_cast<unsigned>((ncols + ptar::SY_BN - 1) / ptar::SY_BN));
+  ptar::gwb_synth_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(G, A, lda, Zm, npts, J, ncols, lower_tri);
+  return check_launch("ptar_gwb_synth");
+}
+
+int ptar_generate(const ptar_gen_params* pp, void* stream) {
+  if (!pp) return fail(-1, "ptar_generate: null params%s");
+  const ptar_gen_params& p = *pp;
+  if (!p.out || !p.tiles || p.n_tiles <= 0 || p.nreal <= 0 || p.n_psr <= 0)
+    return fail(-1, "ptar_generate: bad geometry%s");
+  if ((p.ld_out & 3) || (reinterpret_cast<uintptr_t>(p.out) & 31)) return fail(-2, "ptar_generate: out must be 32-byte aligned, ld_out %% 4 == 0%s");
+  if ((p.flags & PTAR_F_RED) && (p.J <= 0 || (p.J & 1) || !p.Ftile || !p.rn_scale || !p.rn_omega))
+    return fail(-2, "ptar_generate: red noise needs even J, Ftile, rn_scale, rn_omega%s");
+  if ((p.flags & PTAR_F_WHITE) && (!p.w1 || (!(p.flags & PTAR_F_WHITE1) && !p.w2)))
+    return fail(-2, "ptar_generate: white noise needs w1/w2%s");
+  if ((p.flags & PTAR_F_ECORR) && (!p.ep_ecorr || !p.ep_bucket)) return fail(-2, "ptar_generate: ECORR needs ep_ecorr/ep_bucket%s");
+  if ((p.flags & (PTAR_F_ECORR | PTAR_F_RED)) && (!p.eloc || !p.dtau)) return fail(-2, "ptar_generate: epoch terms need eloc/dtau%s");
+  if ((p.flags & PTAR_F_GWB) && (!p.G || p.npts <= 1 || !p.gidx || !p.gw)) return fail(-2, "ptar_generate: GWB needs G, gidx, gw%s");
+  if ((p.flags & PTAR_F_DET) && !p.det) return fail(-2, "ptar_generate: DET needs det%s");
+  const bool inject = p.z1 || p.z2 || p.zb || p.zrn;
+  if (inject) {
+    if ((p.flags & PTAR_F_WHITE) && (!p.z1 || (!(p.flags & PTAR_F_WHITE1) && !p.z2))) return fail(-2, "ptar_generate: injected white draws missing%s");
+    if ((p.flags & PTAR_F_ECORR) && (!p.zb || !p.psr_bucket_off)) return fail(-2, "ptar_generate: injected ECORR draws missing%s");
+    if ((p.flags & PTAR_F_RED) && !p.zrn) return fail(-2, "ptar_generate: injected red-noise draws missing%s");
+  } else if (p.real0 & 3) {
+    return fail(-2, "ptar_generate: real0 must be a multiple of 4%s");
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int rc = p.rc ? p.rc : 16;
+  if (rc == 16) return inject ? launch_gen<16, true>(p, st) : launch_gen<16, false>(p, st);
+  if (rc == 32) return inject ? launch_gen<32, true>(p, st) : launch_gen<32, false>(p, st);
+  return fail(-2, "ptar_generate: rc must be 16 or 32%s");
+}
+
+int ptar_philox_normals(float* out, int kind, int psr, int64_t realization, int64_t idx0, int64_t n, int lane_is_real,
+                        uint64_t seed, void* stream) {
+  if (!out || n < 0) return fail(-1, "ptar_philox_normals: bad argument%s");
+  if (n == 0) return 0;
+  philox_normals_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      out, kind, psr, realization, idx0, n, lane_is_real, seed);
+  return check_launch("ptar_philox_normals");
+}
+
+int ptar_run_job(const ptar_job* job, int64_t real0, int32_t nreal, double* out, void* stream) {
+  if (!job || !out || nreal <= 0) return fail(-1, "ptar_run_job: bad argument%s");
+  ptar_gen_params g = job->gen;
+  g.real0 = real0;
+  g.nreal = nreal;
+  g.out = out;
+  const bool inject = g.z1 || g.z2 || g.zb || g.zrn || job->gwb_zin;
+  if (g.flags & PTAR_F_GWB) {
+    if (!job->M || !job->A || !job->Zm || !job->Gbuf) return fail(-2, "ptar_run_job: GWB buffers missing%s");
+    int rc = ptar_gwb_mix(job->Zm, job->M, inject ? job->gwb_zin : nullptr, g.n_psr, job->Jg, nreal, g.seed, real0, stream);
+    if (rc) return rc;
+    rc = ptar_gwb_synth(job->Gbuf, job->A, job->lda, job->Zm, g.npts, job->Jg, int64_t(nreal) * g.n_psr, job->lower_tri, stream);
+    if (rc) return rc;
+    g.G = job->Gbuf;
+  }
+  return ptar_generate(&g, stream);
+}
+
+int ptar_run_job_to_host(const ptar_job* job, int64_t real0, int64_t nreal, int32_t chunk, double* out_host,
+                         double* dev_buf0, double* dev_buf1, void* stream0, void* stream1) {
+  if (!job || !out_host || !dev_buf0 || !dev_buf1 || chunk <= 0 || (chunk & 3) || nreal <= 0)
+    return fail(-1, "ptar_run_job_to_host: bad argument (chunk must be a positive multiple of 4)%s");
+  cudaStream_t s0 = static_cast<cudaStream_t>(stream0), s1 = static_cast<cudaStream_t>(stream1);
+  cudaEvent_t gen_done[2], copy_done[2];
+  for (int i = 0; i < 2; ++i) {
+    cudaEventCreateWithFlags(&gen_done[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&copy_done[i], cudaEventDisableTiming);
+  }
+  double* bufs[2] = {dev_buf0, dev_buf1};
+  const int64_t ld = job->gen.ld_out;
+  int rc = 0;
+  int64_t done = 0;
+  for (int c = 0; done < nreal; ++c) {
+    const int b = c & 1;
+    const int32_t n = static_cast<int32_t>(nreal - done < chunk ? nreal - done : chunk);
+    if (c >= 2) cudaStreamWaitEvent(s0, copy_done[b], 0);  // buffer free again
+    ptar_job j = *job;
+    if (j.gen.z1) j.gen.z1 += done * ld;
+    if (j.gen.z2) j.gen.z2 += done * ld;
+    if (j.gen.zb) j.gen.zb += done * j.gen.n_bucket_total;
+    if (j.gen.zrn) j.gen.zrn += done * int64_t(j.gen.n_psr) * j.gen.J;
+    if (j.gwb_zin) j.gwb_zin += done * int64_t(j.gen.n_psr) * j.Jg;
+    rc = ptar_run_job(&j, real0 + done, n, bufs[b], s0);
+    if (rc) break;
+    cudaEventRecord(gen_done[b], s0);
+    cudaStreamWaitEvent(s1, gen_done[b], 0);
+    cudaMemcpyAsync(out_host + done * ld, bufs[b], sizeof(double) * size_t(n) * ld, cudaMemcpyDeviceToHost, s1);
+    cudaEventRecord(copy_done[b], s1);
+    done += n;
+  }
+  cudaStreamSynchronize(s1);
+  cudaStreamSynchronize(s0);
+  for (int i = 0; i < 2; ++i) {
+    cudaEventDestroy(gen_done[i]);
+    cudaEventDestroy(copy_done[i]);
+  }
+  if (rc) return rc;
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(-100, "ptar_run_job_to_host: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,228 @@
+// GWB stage kernels (red_noise.py:235-285) and the small dense Cholesky.
+//
+// The reference colours complex white draws with the Cholesky factor of the ORF, scales by
+// sqrt(C(f)), Hermitian-packs, inverse-FFTs (length 2Nf-2 = 2 x prime) and keeps npts samples.
+// All of that is ONE real linear map per pulsar row:  grid = A . z  with
+//   parity mode      A = T  [npts x 2(Nf-2)]  (pruned inverse DFT x sqrt(C)/dt; z = the
+//                    reference's own draws, so results match the reference to fp64 rounding)
+//   throughput mode  A = L  [npts x npts] lower triangular with L L^T = T T^T (same Gaussian
+//                    law from npts instead of 2(Nf-2) draws per pulsar; 10-20x fewer flops)
+// and the ORF mixing M commutes with it, so it is applied to the draws first (ptar_gwb_mix).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ptar.h"
+#include "ptar_rng.cuh"
+
+namespace ptar {
+
+// ---------------------------------------------------------------------------------------
+// Zm[r][p][j] = sum_{q<=p} M[p][q] z[r][q][j]
+// CTA: 32 columns j x 4 realizations (one Philox realization group).  Warp = 4 pulsar rows,
+// lanes = columns; the draws of all pulsars for the 32 columns sit in shared memory.
+constexpr int MIX_JT = 32;
+
+template <bool INJECT>
+__global__ void __launch_bounds__(1024) gwb_mix_kernel(double* __restrict__ Zm, const double* __restrict__ M,
+                                                        const double* __restrict__ zin, int P, int J, int64_t nreal,
+                                                        uint64_t seed, int64_t real0) {
+  extern __shared__ __align__(16) double zs[];  // [P][32][4]
+  const int j0 = blockIdx.x * MIX_JT;
+  const int64_t rbase = int64_t(blockIdx.y) * 4;
+  const int tid = threadIdx.x, nth = blockDim.x;
+  for (int idx = tid; idx < P * MIX_JT; idx += nth) {
+    const int q = idx / MIX_JT, jj = idx % MIX_JT, j = j0 + jj;
+    double z[4] = {0, 0, 0, 0};
+    if (j < J) {
+      if (INJECT) {
+#pragma unroll
+        for (int l = 0; l < 4; ++l)
+          if (rbase + l < nreal) z[l] = zin[((rbase + l) * P + q) * J + j];
+      } else {
+        float n[4];
+        normals4(n, j, PTAR_K_GWB, q, static_cast<uint64_t>(real0 + rbase) >> 2, seed);
+#pragma unroll
+        for (int l = 0; l < 4; ++l) z[l] = static_cast<double>(n[l]);
+      }
+    }
+    double2* d = reinterpret_cast<double2*>(zs + size_t(idx) * 4);
+    d[0] = make_double2(z[0], z[1]);
+    d[1] = make_double2(z[2], z[3]);
+  }
+  __syncthreads();
+  const int lane = tid & 31, warp = tid >> 5, nwarps = nth >> 5;
+  const int j = j0 + lane;
+  for (int pb = warp; pb * 4 < P; pb += nwarps) {
+    const int p0 = pb * 4;
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int l = 0; l < 4; ++l) acc[a][l] = 0.0;
+    const int qmax = min(P, p0 + 4);
+    for (int q = 0; q < qmax; ++q) {
+      const double2 za = *reinterpret_cast<const double2*>(zs + (size_t(q) * MIX_JT + lane) * 4);
+      const double2 zb = *reinterpret_cast<const double2*>(zs + (size_t(q) * MIX_JT + lane) * 4 + 2);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int p = p0 + a;
+        const double m = (p < P && q <= p) ? __ldg(M + size_t(p) * P + q) : 0.0;
+        acc[a][0] = fma(m, za.x, acc[a][0]);
+        acc[a][1] = fma(m, za.y, acc[a][1]);
+        acc[a][2] = fma(m, zb.x, acc[a][2]);
+        acc[a][3] = fma(m, zb.y, acc[a][3]);
+      }
+    }
+    if (j < J) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int p = p0 + a;
+        if (p < P) {
+#pragma unroll
+          for (int l = 0; l < 4; ++l)
+            if (rbase + l < nreal) Zm[((rbase + l) * P + p) * J + j] = acc[a][l];
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// G[c][n] = sum_j A[n][j] * Z[c][j]   (both operands K-contiguous; fp64 FMA pipe)
+// 64x64 tile, BK = 16, 256 threads, 4x4 register micro-tile, register-prefetched next tile.
+constexpr int SY_BM = 64, SY_BN = 64, SY_BK = 16, SY_PAD = 2;
+
+__global__ void __launch_bounds__(256) gwb_synth_kernel(double* __restrict__ G, const double* __restrict__ A,
+                                                         int64_t lda, const double* __restrict__ Z, int npts, int J,
+                                                         int64_t ncols, int lower_tri) {
+  __shared__ __align__(16) double As[SY_BK][SY_BM + SY_PAD];
+  __shared__ __align__(16) double Bs[SY_BK][SY_BN + SY_PAD];
+  const int tid = threadIdx.x;
+  const int n0 = blockIdx.x * SY_BM;
+  const int64_t c0 = int64_t(blockIdx.y) * SY_BN;
+  const int lrow = tid >> 2, lq = (tid & 3) * 4;  // loader: row 0..63, k-quarter 0,4,8,12
+  const int ty = tid >> 4, tx = tid & 15;         // compute: rows n0+ty*4.., cols c0+tx*4..
+  const int kend = lower_tri ? min(J, n0 + SY_BM) : J;
+
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[i][k] = 0.0;
+
+  double ra[4], rb[4];
+  auto fetch = [&](int k0) {
+    const int n = n0 + lrow;
+    const int64_t c = c0 + lrow;
+    const int k = k0 + lq;
+    if (n < npts && k < J) {
+      const double2 u = *reinterpret_cast<const double2*>(A + size_t(n) * lda + k);
+      const double2 v = *reinterpret_cast<const double2*>(A + size_t(n) * lda + k + 2);
+      ra[0] = u.x; ra[1] = u.y; ra[2] = v.x; ra[3] = v.y;
+    } else {
+      ra[0] = ra[1] = ra[2] = ra[3] = 0.0;
+    }
+    if (c < ncols && k < J) {
+      const double2 u = *reinterpret_cast<const double2*>(Z + size_t(c) * J + k);
+      const double2 v = *reinterpret_cast<const double2*>(Z + size_t(c) * J + k + 2);
+      rb[0] = u.x; rb[1] = u.y; rb[2] = v.x; rb[3] = v.y;
+    } else {
+      rb[0] = rb[1] = rb[2] = rb[3] = 0.0;
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < kend; k0 += SY_BK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      As[lq + i][lrow] = ra[i];
+      Bs[lq + i][lrow] = rb[i];
+    }
+    __syncthreads();
+    if (k0 + SY_BK < kend) fetch(k0 + SY_BK);
+#pragma unroll
+    for (int k = 0; k < SY_BK; ++k) {
+      const double2 a01 = *reinterpret_cast<const double2*>(&As[k][ty * 4]);
+      const double2 a23 = *reinterpret_cast<const double2*>(&As[k][ty * 4 + 2]);
+      const double2 b01 = *reinterpret_cast<const double2*>(&Bs[k][tx * 4]);
+      const double2 b23 = *reinterpret_cast<const double2*>(&Bs[k][tx * 4 + 2]);
+      const double a[4] = {a01.x, a01.y, a23.x, a23.y};
+      const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int m = 0; m < 4; ++m) acc[i][m] = fma(a[i], b[m], acc[i][m]);
+    }
+    __syncthreads();
+  }
+  // G[c][n]: thread owns n = n0+ty*4..+3 (contiguous) for 4 columns
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const int64_t c = c0 + tx * 4 + m;
+    if (c >= ncols) continue;
+    const int n = n0 + ty * 4;
+    double* g = G + size_t(c) * npts + n;
+    if (n + 3 < npts && ((size_t(c) * npts + n) & 1) == 0) {
+      *reinterpret_cast<double2*>(g) = make_double2(acc[0][m], acc[1][m]);
+      *reinterpret_cast<double2*>(g + 2) = make_double2(acc[2][m], acc[3][m]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (n + i < npts) g[i] = acc[i][m];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Lower Cholesky, one CTA per matrix, left-looking; every inner product is a warp-shuffle
+// reduction (north_star: "warp-shuffle reductions for the small dense Cholesky").
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(256) cholesky_kernel(double* __restrict__ Lall, const double* __restrict__ Aall,
+                                                        int n, int* __restrict__ info) {
+  double* L = Lall + size_t(blockIdx.x) * n * n;
+  const double* A = Aall + size_t(blockIdx.x) * n * n;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  __shared__ double s_diag;
+  __shared__ int s_bad;
+  if (tid == 0) s_bad = 0;
+  for (int idx = tid; idx < n * n; idx += blockDim.x) {
+    const int i = idx / n, j = idx % n;
+    L[idx] = (j <= i) ? A[idx] : 0.0;
+  }
+  __syncthreads();
+  for (int j = 0; j < n; ++j) {
+    if (warp == 0) {
+      double s = 0.0;
+      for (int k = lane; k < j; k += 32) s = fma(L[size_t(j) * n + k], L[size_t(j) * n + k], s);
+      s = warp_sum(s);
+      if (lane == 0) {
+        const double d = L[size_t(j) * n + j] - s;
+        if (!(d > 0.0)) {
+          s_bad = j + 1;
+          s_diag = 1.0;
+        } else {
+          s_diag = sqrt(d);
+        }
+      }
+    }
+    __syncthreads();
+    if (s_bad) break;
+    const double ljj = s_diag;
+    for (int i = j + 1 + warp; i < n; i += nwarps) {
+      double s = 0.0;
+      for (int k = lane; k < j; k += 32) s = fma(L[size_t(i) * n + k], L[size_t(j) * n + k], s);
+      s = warp_sum(s);
+      if (lane == 0) L[size_t(i) * n + j] = (L[size_t(i) * n + j] - s) / ljj;
+    }
+    if (tid == 0) L[size_t(j) * n + j] = ljj;
+    __syncthreads();
+  }
+  if (tid == 0 && info) info[blockIdx.x] = s_bad;
+}
+
+}  // namespace ptar

@@ -98,13 +98,20 @@ class TOAs:
     def get_flag_value(self, flagid):
         return [f.get(flagid) for f in self.table["flags"]]
 
+    # PINT reports first/last MJD from its own (clock-corrected) columns; a caller that needs to
+    # reproduce a PINT-made data set's GWB grid exactly can pin them here.
+    first_MJD_override = None
+    last_MJD_override = None
+
     @property
     def first_MJD(self):
-        return _Scalar(float(np.min(self.table["tdbld"])))
+        v = self.first_MJD_override
+        return _Scalar(float(np.min(self.table["tdbld"])) if v is None else float(v))
 
     @property
     def last_MJD(self):
-        return _Scalar(float(np.max(self.table["tdbld"])))
+        v = self.last_MJD_override
+        return _Scalar(float(np.max(self.table["tdbld"])) if v is None else float(v))
 
     def adjust_TOAs(self, delta):
         """Shift the TOAs by ``delta`` (TimeArray, or plain array of days)."""
