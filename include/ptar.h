@@ -81,12 +81,13 @@ typedef struct {
   const double*   w2;    /* efac*equad (t2equad) or equad (tnequad) [s]                  */
   const double*   dtau;  /* t - t_ref(epoch) [s]                                         */
   const uint16_t* eloc;  /* kernel-epoch index local to the tile                         */
-  const uint16_t* gidx;  /* GWB grid interval                                            */
-  const double*   gw;    /* interpolation weight in [0,1]                                */
   const double*   det;   /* deterministic delay [s]                                      */
-  /* per-epoch statics */
+  /* per-epoch statics (an epoch never straddles an ECORR bucket edge or a GWB grid knot) */
   const double*  ep_ecorr;   /* ecorr of the epoch's bucket [s]                          */
   const int32_t* ep_bucket;  /* ECORR bucket id within the pulsar                        */
+  const int32_t* ep_gidx;    /* GWB grid interval j of the epoch                         */
+  const double*  ep_gw;      /* (t_ref - ut[j]) / (ut[j+1] - ut[j])                      */
+  const double*  ep_ginv;    /* 1 / (ut[j+1] - ut[j])  [1/s]                             */
   const int64_t* psr_bucket_off; /* [n_psr]: offset of each pulsar in the injected zb axis */
   const double*  Ftile;      /* [n_tiles][J][64]: basis at epoch reference times          */
   /* per-pulsar red-noise statics */
@@ -107,7 +108,7 @@ typedef struct {
   double* out;
   int64_t ld_out;
   int32_t nreal;
-  int32_t rc;         /* realizations per CTA: 16 or 32 (0 = default)                    */
+  int32_t rc;         /* realizations per CTA: 16 (0 = default)                          */
 } ptar_gen_params;
 
 int         ptar_version(void);
@@ -144,11 +145,12 @@ int ptar_gwb_synth(double* G, const double* A, int64_t lda, const double* Zm, in
 int ptar_generate(const ptar_gen_params* p, void* stream);
 
 /* Raw throughput-mode normals (fp32 Box-Muller of Philox4x32-10), for tests:
- * out[k] = normal(kind, psr, realization, idx0 + k), k < n. `lane_is_real` selects which of
- * the two counter groupings the kernels use (0: white, lanes = 4 consecutive idx;
- * 1: ecorr/red/gwb, lanes = 4 consecutive realizations). */
+ * out[k] = normal(kind, psr, realization, idx0 + k), k < n.  Counter = (idx, kind | psr << 8,
+ * realization >> 2); the four outputs of a counter are realizations 4g .. 4g+3, so a shard of
+ * realizations is reproduced bit-for-bit wherever it is generated.  idx = TOA index within the
+ * pulsar (white), ECORR bucket, Fourier column (red), grid column (GWB). */
 int ptar_philox_normals(float* out, int kind, int psr, int64_t realization, int64_t idx0,
-                        int64_t n, int lane_is_real, uint64_t seed, void* stream);
+                        int64_t n, uint64_t seed, void* stream);
 
 /* End-to-end job: GWB mix + synth + generate for realizations [real0, real0+nreal), then
  * (ptar_run_job_to_host) copy the residuals to pinned host memory, chunk by chunk, with the

@@ -34,10 +34,12 @@ def philox4x32_10(c0, c1, c2, c3, seed):
 
 
 def _box_muller(a, b):
-    u1 = (a.astype(np.float32) + np.float32(0.5)) * np.float32(2.3283064365386963e-10)
-    u2 = (b.astype(np.float32) + np.float32(0.5)) * np.float32(2.3283064365386963e-10)
-    r = np.sqrt(-2.0 * np.log(u1.astype(np.float64)))
-    th = (np.float32(6.2831853071795865) * u2).astype(np.float64)
+    """ptar_rng.cuh::box_muller with the transcendental functions in float64."""
+    af = a.astype(np.float32) + np.float32(0.5)
+    r2 = np.maximum(44.361419555836500 - 1.3862943611198906 * np.log2(af.astype(np.float64)), 0.0)
+    r = np.sqrt(r2)
+    th = (b.astype(np.float32).astype(np.float64) * np.float64(np.float32(1.4629180792671596e-9))
+          + np.float64(np.float32(7.3145903963357980e-10))).astype(np.float32).astype(np.float64)  # = fmaf
     return r * np.cos(th), r * np.sin(th)
 
 
@@ -52,14 +54,7 @@ def normals4(block, kind, psr, rfield, seed):
     return np.stack([n0, n1, n2, n3], axis=-1)
 
 
-def white_normals(kind, psr, realization, n, seed):
-    """White-noise stream: element idx of pulsar ``psr`` for one realization (lanes = idx & 3)."""
-    nb = (n + 3) // 4
-    z = normals4(np.arange(nb), kind, psr, int(realization), seed).reshape(-1)
-    return z[:n]
-
-
-def lane_normals(kind, psr, realization, n, seed):
-    """ECORR / red / GWB streams: element idx, lanes = realization & 3."""
-    z = normals4(np.arange(n), kind, psr, int(realization) >> 2, seed)
+def normals(kind, psr, realization, n, seed, idx0=0):
+    """Elements idx0 .. idx0+n-1 of stream (kind, psr) for one global realization id."""
+    z = normals4(np.arange(idx0, idx0 + n), kind, psr, int(realization) >> 2, seed)
     return z[:, int(realization) & 3]

@@ -34,9 +34,9 @@ class GenParams(C.Structure):
         ("n_psr", C.c_int32), ("n_tiles", C.c_int32), ("J", C.c_int32), ("npts", C.c_int32),
         ("flags", C.c_uint32), ("rn_convention", C.c_int32),
         ("tiles", C.c_void_p),
-        ("w1", C.c_void_p), ("w2", C.c_void_p), ("dtau", C.c_void_p), ("eloc", C.c_void_p),
-        ("gidx", C.c_void_p), ("gw", C.c_void_p), ("det", C.c_void_p),
-        ("ep_ecorr", C.c_void_p), ("ep_bucket", C.c_void_p), ("psr_bucket_off", C.c_void_p), ("Ftile", C.c_void_p),
+        ("w1", C.c_void_p), ("w2", C.c_void_p), ("dtau", C.c_void_p), ("eloc", C.c_void_p), ("det", C.c_void_p),
+        ("ep_ecorr", C.c_void_p), ("ep_bucket", C.c_void_p), ("ep_gidx", C.c_void_p), ("ep_gw", C.c_void_p),
+        ("ep_ginv", C.c_void_p), ("psr_bucket_off", C.c_void_p), ("Ftile", C.c_void_p),
         ("rn_scale", C.c_void_p), ("rn_omega", C.c_void_p),
         ("G", C.c_void_p),
         ("z1", C.c_void_p), ("z2", C.c_void_p), ("zb", C.c_void_p), ("zrn", C.c_void_p),
@@ -76,7 +76,7 @@ def lib():
     L.ptar_gwb_mix.argtypes = [vp, vp, vp, i32, i32, i64, u64, i64, vp]
     L.ptar_gwb_synth.argtypes = [vp, vp, i64, vp, i32, i32, i64, i32, vp]
     L.ptar_generate.argtypes = [C.POINTER(GenParams), vp]
-    L.ptar_philox_normals.argtypes = [vp, i32, i32, i64, i64, i64, i32, u64, vp]
+    L.ptar_philox_normals.argtypes = [vp, i32, i32, i64, i64, i64, u64, vp]
     L.ptar_run_job.argtypes = [C.POINTER(Job), i64, C.c_int32, vp, vp]
     L.ptar_run_job_to_host.argtypes = [C.POINTER(Job), i64, i64, C.c_int32, vp, vp, vp, vp, vp]
     for name in EXPORTS:

@@ -88,18 +88,12 @@ __global__ void cgw_kernel(double* __restrict__ out, const double* __restrict__ 
 }
 
 __global__ void philox_normals_kernel(float* __restrict__ out, int kind, int psr, int64_t realization, int64_t idx0,
-                                      int64_t n, int lane_is_real, uint64_t seed) {
+                                      int64_t n, uint64_t seed) {
   const int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const int64_t idx = idx0 + k;
   float z[4];
-  if (lane_is_real) {
-    ptar::normals4(z, static_cast<uint32_t>(idx), kind, psr, static_cast<uint64_t>(realization) >> 2, seed);
-    out[k] = z[realization & 3];
-  } else {
-    ptar::normals4(z, static_cast<uint32_t>(idx >> 2), kind, psr, static_cast<uint64_t>(realization), seed);
-    out[k] = z[idx & 3];
-  }
+  ptar::normals4(z, static_cast<uint32_t>(idx0 + k), kind, psr, static_cast<uint64_t>(realization) >> 2, ptar::philox_keys(seed));
+  out[k] = z[realization & 3];
 }
 
 template <int RC, bool INJECT>
@@ -111,8 +105,9 @@ int launch_gen(const ptar_gen_params& p, cudaStream_t st) {
     cudaFuncSetAttribute(ptar::gen_kernel<RC, INJECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
-  const dim3 grid(p.n_tiles, (p.nreal + RC - 1) / RC);
-  ptar::gen_kernel<RC, INJECT><<<grid, ptar::GEN_THREADS, smem, st>>>(p);
+  const dim3 grid((p.nreal + RC - 1) / RC, p.n_tiles);
+  if (grid.y > 65535) return fail(-3, "ptar_generate: more than 65535 tiles%s");
+  ptar::gen_kernel<RC, INJECT><<<grid, ptar::GEN_THREADS, smem, st>>>(p, ptar::philox_keys(p.seed));
   return check_launch("ptar_generate");
 }
 
@@ -192,7 +187,8 @@ int ptar_generate(const ptar_gen_params* pp, void* stream) {
     return fail(-2, "ptar_generate: white noise needs w1/w2%s");
   if ((p.flags & PTAR_F_ECORR) && (!p.ep_ecorr || !p.ep_bucket)) return fail(-2, "ptar_generate: ECORR needs ep_ecorr/ep_bucket%s");
   if ((p.flags & (PTAR_F_ECORR | PTAR_F_RED)) && (!p.eloc || !p.dtau)) return fail(-2, "ptar_generate: epoch terms need eloc/dtau%s");
-  if ((p.flags & PTAR_F_GWB) && (!p.G || p.npts <= 1 || !p.gidx || !p.gw)) return fail(-2, "ptar_generate: GWB needs G, gidx, gw%s");
+  if ((p.flags & PTAR_F_GWB) && (!p.G || p.npts <= 1 || !p.ep_gidx || !p.ep_gw || !p.ep_ginv || !p.eloc || !p.dtau))
+    return fail(-2, "ptar_generate: GWB needs G, ep_gidx, ep_gw, ep_ginv, eloc, dtau%s");
   if ((p.flags & PTAR_F_DET) && !p.det) return fail(-2, "ptar_generate: DET needs det%s");
   const bool inject = p.z1 || p.z2 || p.zb || p.zrn;
   if (inject) {
@@ -205,16 +201,15 @@ int ptar_generate(const ptar_gen_params* pp, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int rc = p.rc ? p.rc : 16;
   if (rc == 16) return inject ? launch_gen<16, true>(p, st) : launch_gen<16, false>(p, st);
-  if (rc == 32) return inject ? launch_gen<32, true>(p, st) : launch_gen<32, false>(p, st);
-  return fail(-2, "ptar_generate: rc must be 16 or 32%s");
+  return fail(-2, "ptar_generate: rc must be 16%s");
 }
 
-int ptar_philox_normals(float* out, int kind, int psr, int64_t realization, int64_t idx0, int64_t n, int lane_is_real,
-                        uint64_t seed, void* stream) {
+int ptar_philox_normals(float* out, int kind, int psr, int64_t realization, int64_t idx0, int64_t n, uint64_t seed,
+                        void* stream) {
   if (!out || n < 0) return fail(-1, "ptar_philox_normals: bad argument%s");
   if (n == 0) return 0;
   philox_normals_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      out, kind, psr, realization, idx0, n, lane_is_real, seed);
+      out, kind, psr, realization, idx0, n, seed);
   return check_launch("ptar_philox_normals");
 }
 

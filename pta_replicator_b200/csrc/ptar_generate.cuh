@@ -7,18 +7,21 @@
 //             + det_i                                  deterministic.py:160-165
 //
 // One CTA = one tile (<=1024 time-sorted TOAs of one pulsar, <=64 kernel-epochs) x RC
-// realizations.  Work that is constant inside an epoch is done once per (epoch, realization)
-// in an "epoch stage" and kept in shared memory:
-//   * the Fourier projection F_e . a_r -- a [64 x J] x [J x 3RC] fp64 GEMM on the FMA pipe
-//     whose three right-hand sides are the coefficient vector and its first two time
-//     derivatives, so that TOAs inside an epoch (sub-band TOAs <1 s apart) are reached by a
-//     2nd-order Taylor step whose remainder is below fp64 rounding of the direct sum (the
-//     host picks nd per tile from |omega_max * dt|; single-TOA epochs are exact, nd = 1);
+// realizations.  Everything that is smooth inside an epoch is evaluated once per
+// (epoch, realization) in an "epoch stage" and kept in shared memory as a quadratic in
+// dt = t - t_ref(epoch):
+//   * the Fourier projection F_e . a_r -- a [64 x J] x [J x 3RC] fp64 GEMM on the FMA pipe whose
+//     three right-hand sides are the coefficient vector and its first two time derivatives, so
+//     TOAs inside an epoch (sub-band TOAs < 1 s apart) are reached by a 2nd-order Taylor step whose
+//     remainder is below fp64 rounding of the direct sum (the host picks nd per tile from
+//     |omega_max dt|; single-TOA epochs are exact, nd = 1);
+//   * the GWB grid interpolation (epochs never straddle a grid knot, so it is exactly linear in dt);
 //   * the ECORR draw of the epoch's bucket.
-// The basis tile F [J][64] is fetched with one bulk-async (TMA) copy that overlaps the Philox
-// generation of the coefficients.  The "TOA stage" then streams the realizations: per TOA two
-// Philox/Box-Muller normals, a 3-term Horner step, a 2-point GWB interpolation read through
-// L1, and one 32-byte store -- the only HBM traffic that scales with R x N_toa.
+// The basis tile F [J][64] arrives by one bulk-async (TMA) copy that overlaps the Philox generation
+// of the coefficients.  The "TOA stage" then streams the realizations: one thread owns a TOA and
+// four consecutive realizations (= the four outputs of one Philox counter), so per 4 outputs it
+// spends two Philox calls, four Box-Muller pairs, six 128-bit shared loads, a Horner step and four
+// coalesced 8-byte stores -- the only HBM traffic that scales with R x N_toa.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -29,11 +32,18 @@
 namespace ptar {
 
 constexpr int GEN_THREADS = 256;
+#ifndef GEN_MIN_CTAS
+#define GEN_MIN_CTAS 3
+#endif
 constexpr int EP = PTAR_TILE_EPOCHS;  // 64
 
+__host__ __device__ constexpr int gen_css(int RC) { return 3 * RC + 2; }  // even (16-B rows), 4e-word bank skew
+
 __host__ __device__ inline size_t gen_smem_bytes(int J, int RC) {
-  // mbarrier (16 B) + Fs[J][64] + As[3][J][RC] + Cs[64][3RC+1]
-  return 16 + sizeof(double) * (size_t(J) * EP + size_t(3) * J * RC + size_t(EP) * (3 * RC + 1));
+  // mbarrier (16 B) + max(Fs[J][64] + As[3][J][RC], Cs[64][css])  (Cs aliases the GEMM operands)
+  const size_t ops = size_t(J) * EP + size_t(3) * J * RC;
+  const size_t cs = size_t(EP) * gen_css(RC);
+  return 16 + sizeof(double) * (ops > cs ? ops : cs);
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -41,28 +51,38 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 
 template <int RC, bool INJECT>
-__global__ void __launch_bounds__(GEN_THREADS, (RC <= 16 ? 2 : 1)) gen_kernel(const ptar_gen_params P) {
+__global__ void __launch_bounds__(GEN_THREADS, GEN_MIN_CTAS) gen_kernel(const ptar_gen_params P, const PhiloxKeys K) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
   double* Fs = reinterpret_cast<double*>(smem_raw + 16);
   const int J = P.J;
   double* As = Fs + size_t(J) * EP;
-  double* Cs = As + size_t(3) * J * RC;
-  constexpr int CSS = 3 * RC + 1;  // odd stride: epochs land in different banks
+  double* Cs = Fs;  // written only after the GEMM has consumed Fs / As
+  constexpr int CSS = gen_css(RC);
+  constexpr int RG = RC / 4;
 
   const int tid = threadIdx.x;
-  const ptar_tile tile = P.tiles[blockIdx.x];
-  const int r0 = blockIdx.y * RC;                 // first realization (local to this call)
+  const ptar_tile tile = P.tiles[blockIdx.y];   // x = realization chunk (fastest): the CTAs that share a
+  const int r0 = blockIdx.x * RC;               // tile's statics and basis run together and hit L2  // first realization (local to this call)
   const int nr = min(RC, P.nreal - r0);
   const uint32_t flags = P.flags;
   const bool has_red = (flags & PTAR_F_RED) && J > 0;
   const bool has_ecorr = (flags & PTAR_F_ECORR) != 0;
-  const bool has_epoch = has_red || has_ecorr;
-  const int nd = has_red ? tile.nd : 1;
+  const bool has_gwb = (flags & PTAR_F_GWB) && P.npts > 0;
+  const bool has_epoch = has_red || has_ecorr || has_gwb;
+  const int nd = tile.nd;
   const uint32_t psr = static_cast<uint32_t>(tile.psr);
-  const uint64_t rgroup0 = static_cast<uint64_t>(P.real0 + r0) >> 2;  // realization-lane streams
+  const uint64_t rgroup0 = static_cast<uint64_t>(P.real0 + r0) >> 2;
 
   // ---- epoch stage -------------------------------------------------------------------
+  // GEMM ownership: thread -> realization rr, epochs e0..e0+3
+  static_assert(RC == 16, "thread -> (realization, 4 epochs) ownership below assumes RC == 16");
+  const int rr = tid & 15;
+  const int e0 = (tid >> 4) * 4;
+  double acc[4][3];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = 0.0;
+
   if (has_red) {
     if (tid == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
@@ -71,7 +91,7 @@ __global__ void __launch_bounds__(GEN_THREADS, (RC <= 16 ? 2 : 1)) gen_kernel(co
     __syncthreads();
     if (tid == 0) {
       const uint32_t bytes = static_cast<uint32_t>(sizeof(double) * J * EP);
-      const double* src = P.Ftile + size_t(blockIdx.x) * J * EP;
+      const double* src = P.Ftile + size_t(blockIdx.y) * J * EP;
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes)
                    : "memory");
       asm volatile(
@@ -88,18 +108,17 @@ __global__ void __launch_bounds__(GEN_THREADS, (RC <= 16 ? 2 : 1)) gen_kernel(co
         As[idx] = (r < nr) ? scale[j] * P.zrn[(size_t(r0 + r) * P.n_psr + psr) * J + j] : 0.0;
       }
     } else {
-      constexpr int RG = RC / 4;
       for (int idx = tid; idx < J * RG; idx += GEN_THREADS) {
         const int j = idx / RG, rg = idx % RG;
         float n[4];
-        normals4(n, j, PTAR_K_RED, psr, rgroup0 + rg, P.seed);
+        normals4(n, j, PTAR_K_RED, psr, rgroup0 + rg, K);
         const double s = scale[j];
 #pragma unroll
         for (int l = 0; l < 4; ++l) As[j * RC + rg * 4 + l] = s * static_cast<double>(n[l]);
       }
     }
     __syncthreads();
-    if (nd > 1) {  // time derivatives of the coefficient vector (folded 1/2 in the 2nd)
+    if (nd > 1) {  // time derivatives of the coefficient vector (1/2 folded into the 2nd)
       const double* om = P.rn_omega + size_t(psr) * (J / 2);
       const double sgn_even = P.rn_convention ? 1.0 : -1.0;
       for (int idx = tid; idx < J * RC; idx += GEN_THREADS) {
@@ -109,44 +128,9 @@ __global__ void __launch_bounds__(GEN_THREADS, (RC <= 16 ? 2 : 1)) gen_kernel(co
         As[J * RC + idx] = ((j & 1) ? -sgn_even : sgn_even) * w * partner;
         As[2 * J * RC + idx] = -0.5 * w * w * As[idx];
       }
+      __syncthreads();
     }
-  }
-  if (has_epoch) {
-    // Cs[e][r][0] starts from the ECORR draw of the epoch's bucket (or 0)
-    if (has_ecorr) {
-      if (INJECT) {
-        for (int idx = tid; idx < EP * RC; idx += GEN_THREADS) {
-          const int e = idx / RC, r = idx % RC;
-          double v = 0.0;
-          if (e < tile.n_ep && r < nr) {
-            const int ge = tile.ep_start + e;
-            v = P.ep_ecorr[ge] * P.zb[size_t(r0 + r) * P.n_bucket_total + P.psr_bucket_off[psr] + P.ep_bucket[ge]];
-          }
-          Cs[e * CSS + r * 3] = v;
-        }
-      } else {
-        constexpr int RG = RC / 4;
-        for (int idx = tid; idx < EP * RG; idx += GEN_THREADS) {
-          const int e = idx / RG, rg = idx % RG;
-          float n[4] = {0.f, 0.f, 0.f, 0.f};
-          double ec = 0.0;
-          if (e < tile.n_ep) {
-            const int ge = tile.ep_start + e;
-            ec = P.ep_ecorr[ge];
-            normals4(n, P.ep_bucket[ge], PTAR_K_ECORR, psr, rgroup0 + rg, P.seed);
-          }
-#pragma unroll
-          for (int l = 0; l < 4; ++l) Cs[e * CSS + (rg * 4 + l) * 3] = ec * static_cast<double>(n[l]);
-        }
-      }
-    } else {
-      for (int idx = tid; idx < EP * RC; idx += GEN_THREADS) Cs[(idx / RC) * CSS + (idx % RC) * 3] = 0.0;
-    }
-    __syncthreads();
-  }
-  if (has_red) {
-    // wait for the basis tile
-    {
+    {  // wait for the basis tile
       uint32_t done = 0;
       while (!done) {
         asm volatile(
@@ -158,15 +142,7 @@ __global__ void __launch_bounds__(GEN_THREADS, (RC <= 16 ? 2 : 1)) gen_kernel(co
             : "memory");
       }
     }
-    // C[e][r][d] += sum_j F[j][e] * A[d][j][r]; thread = 4 epochs x RPT realizations x nd
-    constexpr int RPT = RC / 16;
-    const int rl = (tid & 15) * RPT;
-    const int e0 = (tid >> 4) * 4;
-    double acc[4][RPT][3];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int u = 0; u < RPT; ++u) acc[i][u][0] = acc[i][u][1] = acc[i][u][2] = 0.0;
+    // C[e][r][d] = sum_j F[j][e] * A[d][j][r]
     if (e0 < tile.n_ep) {
       for (int j = 0; j < J; ++j) {
         const double2 f01 = *reinterpret_cast<const double2*>(Fs + j * EP + e0);
@@ -175,113 +151,138 @@ __global__ void __launch_bounds__(GEN_THREADS, (RC <= 16 ? 2 : 1)) gen_kernel(co
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
           if (d < nd) {
-            double a[RPT];
+            const double a = As[(d * J + j) * RC + rr];
 #pragma unroll
-            for (int u = 0; u < RPT; ++u) a[u] = As[(d * J + j) * RC + rl + u];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-              for (int u = 0; u < RPT; ++u) acc[i][u][d] = fma(f[i], a[u], acc[i][u][d]);
+            for (int i = 0; i < 4; ++i) acc[i][d] = fma(f[i], a, acc[i][d]);
           }
         }
       }
+    }
+    __syncthreads();  // everyone is done reading Fs / As: Cs may overwrite them
+  }
+  if (has_epoch) {
+    // GWB grid interpolation at the epoch reference time and its slope (exactly linear inside the epoch)
+    if (has_gwb && rr < nr) {
+      const double* Gr = P.G + (size_t(r0 + rr) * P.n_psr + psr) * P.npts;
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int u = 0; u < RPT; ++u) {
-          double* c = Cs + (e0 + i) * CSS + (rl + u) * 3;
-          c[0] += acc[i][u][0];
-          c[1] = acc[i][u][1];
-          c[2] = acc[i][u][2];
+      for (int i = 0; i < 4; ++i) {
+        const int e = e0 + i;
+        if (e < tile.n_ep) {
+          const int ge = tile.ep_start + e;
+          const int j = P.ep_gidx[ge];
+          const double g0 = __ldg(Gr + j), dg = __ldg(Gr + j + 1) - g0;
+          acc[i][0] += fma(P.ep_gw[ge], dg, g0);
+          acc[i][1] += dg * P.ep_ginv[ge];
         }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double* c = Cs + (e0 + i) * CSS + rr * 3;
+      c[0] = acc[i][0];
+      c[1] = acc[i][1];
+      c[2] = acc[i][2];
     }
     __syncthreads();
+    if (has_ecorr) {
+      if (INJECT) {
+        for (int idx = tid; idx < tile.n_ep * RC; idx += GEN_THREADS) {
+          const int e = idx / RC, r = idx % RC;
+          if (r < nr) {
+            const int ge = tile.ep_start + e;
+            Cs[e * CSS + r * 3] +=
+                P.ep_ecorr[ge] * P.zb[size_t(r0 + r) * P.n_bucket_total + P.psr_bucket_off[psr] + P.ep_bucket[ge]];
+          }
+        }
+      } else {
+        for (int idx = tid; idx < tile.n_ep * RG; idx += GEN_THREADS) {
+          const int e = idx / RG, rg = idx % RG;
+          const int ge = tile.ep_start + e;
+          const double ec = P.ep_ecorr[ge];
+          float n[4];
+          normals4(n, P.ep_bucket[ge], PTAR_K_ECORR, psr, rgroup0 + rg, K);
+#pragma unroll
+          for (int l = 0; l < 4; ++l) Cs[e * CSS + (rg * 4 + l) * 3] += ec * static_cast<double>(n[l]);
+        }
+      }
+      __syncthreads();
+    }
   }
 
   // ---- TOA stage ---------------------------------------------------------------------
-  const int t4 = tid * 4;
-  if (t4 >= tile.n_toa) return;
-  const size_t gi = size_t(tile.toa_start) + t4;
-  double w1[4] = {0, 0, 0, 0}, w2[4] = {0, 0, 0, 0}, dt[4] = {0, 0, 0, 0}, gw[4] = {0, 0, 0, 0}, det[4] = {0, 0, 0, 0};
-  int el[4] = {0, 0, 0, 0}, gx[4] = {0, 0, 0, 0};
-  if (flags & PTAR_F_WHITE) {
-    const double4 a = *reinterpret_cast<const double4*>(P.w1 + gi);
-    w1[0] = a.x; w1[1] = a.y; w1[2] = a.z; w1[3] = a.w;
-    if (!(flags & PTAR_F_WHITE1)) {
-      const double4 b = *reinterpret_cast<const double4*>(P.w2 + gi);
-      w2[0] = b.x; w2[1] = b.y; w2[2] = b.z; w2[3] = b.w;
-    }
-  }
-  if (has_epoch) {
-    const ushort4 e = *reinterpret_cast<const ushort4*>(P.eloc + gi);
-    el[0] = e.x; el[1] = e.y; el[2] = e.z; el[3] = e.w;
-    if (nd > 1) {
-      const double4 a = *reinterpret_cast<const double4*>(P.dtau + gi);
-      dt[0] = a.x; dt[1] = a.y; dt[2] = a.z; dt[3] = a.w;
-    }
-  }
-  const bool has_gwb = (flags & PTAR_F_GWB) && P.npts > 0;
-  if (has_gwb) {
-    const ushort4 g = *reinterpret_cast<const ushort4*>(P.gidx + gi);
-    gx[0] = g.x; gx[1] = g.y; gx[2] = g.z; gx[3] = g.w;
-    const double4 a = *reinterpret_cast<const double4*>(P.gw + gi);
-    gw[0] = a.x; gw[1] = a.y; gw[2] = a.z; gw[3] = a.w;
-  }
-  if (flags & PTAR_F_DET) {
-    const double4 a = *reinterpret_cast<const double4*>(P.det + gi);
-    det[0] = a.x; det[1] = a.y; det[2] = a.z; det[3] = a.w;
-  }
-  const bool two_draws = (flags & PTAR_F_WHITE) && !(flags & PTAR_F_WHITE1);
-  const uint32_t wblock = static_cast<uint32_t>(tile.toa_local0 + t4) >> 2;
-  const int nvalid = min(4, tile.n_toa - t4);
-
-  for (int r = 0; r < nr; ++r) {
-    double v[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = det[k];
-    if (has_epoch) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const double* c = Cs + el[k] * CSS + r * 3;
-        v[k] += (nd > 1) ? fma(dt[k], fma(dt[k], c[2], c[1]), c[0]) : c[0];
+  const bool has_white = (flags & PTAR_F_WHITE) != 0;
+  const bool two_draws = has_white && !(flags & PTAR_F_WHITE1);
+  const bool has_det = (flags & PTAR_F_DET) != 0;
+  const size_t ld = static_cast<size_t>(P.ld_out);
+  for (int tt = tid; tt < tile.n_toa; tt += GEN_THREADS) {
+    const size_t gi = size_t(tile.toa_start) + tt;
+    // statics of this TOA (their latency is covered by the first Philox evaluation below)
+    const double w1 = has_white ? P.w1[gi] : 0.0;
+    const double w2 = two_draws ? P.w2[gi] : 0.0;
+    const double det = has_det ? P.det[gi] : 0.0;
+    const double dt = (has_epoch && nd > 1) ? P.dtau[gi] : 0.0;
+    const int el = has_epoch ? static_cast<int>(P.eloc[gi]) : 0;
+    const uint32_t wblock = static_cast<uint32_t>(tile.toa_local0 + tt);
+    double* orow = P.out + size_t(r0) * ld + gi;
+#pragma unroll 1
+    for (int rg = 0; rg * 4 < nr; ++rg, orow += 4 * ld) {
+      float n1[4] = {0.f, 0.f, 0.f, 0.f}, n2[4] = {0.f, 0.f, 0.f, 0.f};
+      if (!INJECT && has_white) {
+        normals4(n1, wblock, PTAR_K_WHITE1, psr, rgroup0 + rg, K);
+        if (two_draws) normals4(n2, wblock, PTAR_K_WHITE2, psr, rgroup0 + rg, K);
       }
-    }
-    if (has_gwb) {
-      const double* Gr = P.G + (size_t(r0 + r) * P.n_psr + psr) * P.npts;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const double g0 = __ldg(Gr + gx[k]), g1 = __ldg(Gr + gx[k] + 1);
-        v[k] += fma(gw[k], g1 - g0, g0);
-      }
-    }
-    if (flags & PTAR_F_WHITE) {
-      if (INJECT) {
-        const double4 a = *reinterpret_cast<const double4*>(P.z1 + size_t(r0 + r) * P.ld_out + gi);
-        v[0] = fma(w1[0], a.x, v[0]); v[1] = fma(w1[1], a.y, v[1]);
-        v[2] = fma(w1[2], a.z, v[2]); v[3] = fma(w1[3], a.w, v[3]);
-        if (two_draws) {
-          const double4 b = *reinterpret_cast<const double4*>(P.z2 + size_t(r0 + r) * P.ld_out + gi);
-          v[0] = fma(w2[0], b.x, v[0]); v[1] = fma(w2[1], b.y, v[1]);
-          v[2] = fma(w2[2], b.z, v[2]); v[3] = fma(w2[3], b.w, v[3]);
+      double v[4] = {0.0, 0.0, 0.0, 0.0};
+      if (has_epoch) {
+        const double2* c2 = reinterpret_cast<const double2*>(Cs + el * CSS + rg * 12);
+        const double2 q0 = c2[0], q1 = c2[1], q2 = c2[2], q3 = c2[3], q4 = c2[4], q5 = c2[5];
+        // (c0,c1,c2) x 4 realizations = q0.x q0.y q1.x | q1.y q2.x q2.y | q3.x q3.y q4.x | q4.y q5.x q5.y
+        if (nd > 1) {
+          v[0] = fma(dt, fma(dt, q1.x, q0.y), q0.x);
+          v[1] = fma(dt, fma(dt, q2.y, q2.x), q1.y);
+          v[2] = fma(dt, fma(dt, q4.x, q3.y), q3.x);
+          v[3] = fma(dt, fma(dt, q5.y, q5.x), q4.y);
+        } else {
+          v[0] = q0.x; v[1] = q1.y; v[2] = q3.x; v[3] = q4.y;
         }
+      }
+      if (has_det) {
+        v[0] += det; v[1] += det; v[2] += det; v[3] += det;
+      }
+      if (has_white) {
+        if (INJECT) {
+#pragma unroll
+          for (int l = 0; l < 4; ++l) {
+            if (rg * 4 + l < nr) {
+              const size_t zi = size_t(r0 + rg * 4 + l) * ld + gi;
+              v[l] = fma(w1, P.z1[zi], v[l]);
+              if (two_draws) v[l] = fma(w2, P.z2[zi], v[l]);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int l = 0; l < 4; ++l) v[l] = fma(w1, static_cast<double>(n1[l]), v[l]);
+          if (two_draws) {
+#pragma unroll
+            for (int l = 0; l < 4; ++l) v[l] = fma(w2, static_cast<double>(n2[l]), v[l]);
+          }
+        }
+      }
+      if (rg * 4 + 4 <= nr) {  // streaming stores: the output is never re-read by this kernel
+        __stcs(orow, v[0]);
+        __stcs(orow + ld, v[1]);
+        __stcs(orow + 2 * ld, v[2]);
+        __stcs(orow + 3 * ld, v[3]);
       } else {
-        const uint64_t rid = static_cast<uint64_t>(P.real0 + r0 + r);
-        float n[4];
-        normals4(n, wblock, PTAR_K_WHITE1, psr, rid, P.seed);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = fma(w1[k], static_cast<double>(n[k]), v[k]);
-        if (two_draws) {
-          normals4(n, wblock, PTAR_K_WHITE2, psr, rid, P.seed);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) v[k] = fma(w2[k], static_cast<double>(n[k]), v[k]);
-        }
+        for (int l = 0; l < 4; ++l)
+          if (rg * 4 + l < nr) __stcs(orow + l * ld, v[l]);
       }
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (k >= nvalid) v[k] = 0.0;
-    double* o = P.out + size_t(r0 + r) * P.ld_out + gi;
-    *reinterpret_cast<double4*>(o) = make_double4(v[0], v[1], v[2], v[3]);
+  }
+  // alignment slots after a pulsar's last TOA are written as zeros
+  const int n_pad = ((tile.n_toa + 3) & ~3) - tile.n_toa;
+  if (tid < n_pad) {
+    for (int r = 0; r < nr; ++r) P.out[size_t(r0 + r) * ld + tile.toa_start + tile.n_toa + tid] = 0.0;
   }
 }
 

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(1024) gwb_mix_kernel(double* __restrict__ Zm, 
           if (rbase + l < nreal) z[l] = zin[((rbase + l) * P + q) * J + j];
       } else {
         float n[4];
-        normals4(n, j, PTAR_K_GWB, q, static_cast<uint64_t>(real0 + rbase) >> 2, seed);
+        normals4(n, j, PTAR_K_GWB, q, static_cast<uint64_t>(real0 + rbase) >> 2, philox_keys(seed));
 #pragma unroll
         for (int l = 0; l < 4; ++l) z[l] = static_cast<double>(n[l]);
       }

@@ -6,38 +6,54 @@
 
 namespace ptar {
 
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
+// The ten round keys (k + i*W) depend only on the seed: computed once per kernel and kept in
+// registers / uniform registers so a round is 2 IMAD.WIDE + 2 LOP3.
+struct PhiloxKeys {
+  uint32_t k0[10], k1[10];
+};
+
+__host__ __device__ inline PhiloxKeys philox_keys(uint64_t seed) {
+  PhiloxKeys K;
+  uint32_t a = static_cast<uint32_t>(seed), b = static_cast<uint32_t>(seed >> 32);
 #pragma unroll
   for (int i = 0; i < 10; ++i) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-    c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
+    K.k0[i] = a;
+    K.k1[i] = b;
+    a += 0x9E3779B9u;
+    b += 0xBB67AE85u;
+  }
+  return K;
+}
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKeys& K) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * c.x;
+    const uint64_t p1 = static_cast<uint64_t>(0xCD9E8D57u) * c.z;
+    c = make_uint4(static_cast<uint32_t>(p1 >> 32) ^ c.y ^ K.k0[i], static_cast<uint32_t>(p1),
+                   static_cast<uint32_t>(p0 >> 32) ^ c.w ^ K.k1[i], static_cast<uint32_t>(p0));
   }
   return c;
 }
 
-// Two standard normals from two 32-bit words.
+// Two standard normals from two 32-bit words.  u1 = (a + 0.5) 2^-32 in (0, 1], angle = 2 pi (b + 0.5) 2^-32;
+// radius^2 = -2 ln u1 = 64 ln2 - 2 ln2 * log2(a + 0.5).  MUFU.LG2 / MUFU.RSQ / MUFU.SIN / MUFU.COS.
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
-  const float u1 = (static_cast<float>(a) + 0.5f) * 2.3283064365386963e-10f;  // (0, 1]
-  const float u2 = (static_cast<float>(b) + 0.5f) * 2.3283064365386963e-10f;
-  const float r = sqrtf(-2.0f * __logf(u1));
-  float s, c;
-  __sincosf(6.2831853071795865f * u2, &s, &c);
-  n0 = r * c;
-  n1 = r * s;
+  const float af = static_cast<float>(a) + 0.5f;
+  const float r2 = fmaxf(fmaf(__log2f(af), -1.3862943611198906f, 44.361419555836500f), 1e-30f);
+  const float r = r2 * rsqrtf(r2);
+  const float th = fmaf(static_cast<float>(b), 1.4629180792671596e-9f, 7.3145903963357980e-10f);
+  n0 = r * __cosf(th);
+  n1 = r * __sinf(th);
 }
 
-// Counter layout: c.x = block index, c.y = kind | psr << 8, c.z = low word of the
-// realization field, c.w = high word.  White noise: block = idx >> 2, realization field =
-// global realization id, the 4 outputs are idx&~3 .. +3.  Everything else: block = idx,
-// realization field = id >> 2, the 4 outputs are realizations id&~3 .. +3.
+// Counter layout: c.x = element index (TOA within the pulsar / ECORR bucket / Fourier column /
+// grid column), c.y = kind | psr << 8, (c.z, c.w) = global realization id >> 2.  The 4 outputs
+// of a counter are the realizations id&~3 .. +3 of that element.
 __device__ __forceinline__ void normals4(float n[4], uint32_t block, uint32_t kind, uint32_t psr,
-                                         uint64_t rfield, uint64_t seed) {
+                                         uint64_t rfield, const PhiloxKeys& K) {
   const uint4 w = philox4x32_10(make_uint4(block, kind | (psr << 8), static_cast<uint32_t>(rfield),
-                                           static_cast<uint32_t>(rfield >> 32)),
-                                static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+                                           static_cast<uint32_t>(rfield >> 32)), K);
   box_muller(w.x, w.y, n[0], n[1]);
   box_muller(w.z, w.w, n[2], n[3]);
 }

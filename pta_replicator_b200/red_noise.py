@@ -41,12 +41,14 @@ def create_fourier_design_matrix_red(toas: np.ndarray, nmodes: int = 30, Tspan: 
     tp = toas - toas[0] if libstempo_convention else toas
     F = torch.empty((N, 2 * nmodes), dtype=torch.float64, device=dev)
     off = torch.arange(N, dtype=torch.int64, device=dev) * (2 * nmodes)
-    _cabi.check(_cabi.lib().ptar_fourier_basis(F.data_ptr(), off.data_ptr(), 1, torch.from_numpy(tp).to(dev).data_ptr(),
-                                               torch.zeros(N, dtype=torch.int32, device=dev).data_ptr(),
-                                               torch.from_numpy(f.copy()).to(dev).data_ptr(), nmodes,
-                                               int(bool(libstempo_convention)), N, _cabi.current_stream()),
-                "ptar_fourier_basis")
-    return F.cpu().numpy(), np.repeat(f, 2)
+    tp_d = torch.from_numpy(np.ascontiguousarray(tp)).to(dev)
+    psr_d = torch.zeros(N, dtype=torch.int32, device=dev)
+    f_d = torch.from_numpy(np.ascontiguousarray(f, dtype=np.float64)).to(dev)
+    _cabi.check(_cabi.lib().ptar_fourier_basis(F.data_ptr(), off.data_ptr(), 1, tp_d.data_ptr(), psr_d.data_ptr(),
+                                               f_d.data_ptr(), nmodes, int(bool(libstempo_convention)), N,
+                                               _cabi.current_stream()), "ptar_fourier_basis")
+    out = F.cpu().numpy()   # synchronises; the temporaries above stay referenced until here
+    return out, np.repeat(f, 2)
 
 
 def add_red_noise(psr: SimulatedPulsar, log10_amplitude: float, spectral_index: float, components: int = 30,
