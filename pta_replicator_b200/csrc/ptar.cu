@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/ptar.h"
@@ -170,8 +171,22 @@ int ptar_gwb_synth(double* G, const double* A, int64_t lda, const double* Zm, in
                    int lower_tri, void* stream) {
   if (!G || !A || !Zm || npts <= 0 || J <= 0 || ncols <= 0) return fail(-1, "ptar_gwb_synth: bad argument%s");
   if ((J & 3) || (lda & 1) || lda < J) return fail(-2, "ptar_gwb_synth: need J %% 4 == 0 and even lda >= J%s");
-  const dim3 grid((npts + ptar::SY_BM - 1) / ptar::SY_BM, static_cast<unsigned>((ncols + ptar::SY_BN - 1) / ptar::SY_BN));
-  ptar::gwb_synth_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(G, A, lda, Zm, npts, J, ncols, lower_tri);
+  static const bool use_fma = getenv("PTAR_SYNTH_FMA") != nullptr;  // legacy FMA-pipe kernel, kept for A/B runs
+  if (use_fma) {
+    const dim3 grid((npts + ptar::SY_BM - 1) / ptar::SY_BM, static_cast<unsigned>((ncols + ptar::SY_BN - 1) / ptar::SY_BN));
+    ptar::gwb_synth_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(G, A, lda, Zm, npts, J, ncols, lower_tri);
+    return check_launch("ptar_gwb_synth");
+  }
+  const int n_tiles = (npts + ptar::DM_BN - 1) / ptar::DM_BN;
+  const int64_t c_tiles = (ncols + ptar::DM_BC - 1) / ptar::DM_BC;
+  if (c_tiles * n_tiles > 0x7fffffffLL) return fail(-3, "ptar_gwb_synth: grid too large%s");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(ptar::gwb_synth_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ptar::DM_SMEM));
+    attr_set = true;
+  }
+  ptar::gwb_synth_dmma_kernel<<<static_cast<unsigned>(c_tiles * n_tiles), 256, ptar::DM_SMEM, static_cast<cudaStream_t>(stream)>>>(
+      G, A, lda, Zm, npts, J, ncols, lower_tri, static_cast<int>(c_tiles), n_tiles);
   return check_launch("ptar_gwb_synth");
 }
 

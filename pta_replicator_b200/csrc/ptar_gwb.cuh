@@ -174,6 +174,119 @@ __global__ void __launch_bounds__(256) gwb_synth_kernel(double* __restrict__ G, 
 }
 
 // ---------------------------------------------------------------------------------------
+// Same GEMM on the fp64 tensor path (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4; tcgen05 has no fp64
+// kind).  D[c][n] = sum_j Z[c][j] * A[n][j]:  mma A-operand = Z (row-major, K contiguous),
+// B-operand = A^T ("col": K contiguous per n).  CTA tile 128 (c) x 64 (n), BK = 16, 8 warps as
+// 4 (c) x 2 (n), each a 32 x 32 warp tile = 4 x 4 DMMA tiles; operands staged with 16-byte
+// cp.async through a 3-stage ring; rows padded to 20 doubles so the 8x4 fragment loads are
+// conflict free.  The lower-triangular A of the throughput mode makes the n-tiles unequal
+// (k runs to n0+64): the heaviest tiles are scheduled first.
+constexpr int DM_BC = 128, DM_BN = 64, DM_BK = 16, DM_S = DM_BK + 4, DM_STAGES = 3;
+constexpr size_t DM_SMEM = sizeof(double) * DM_STAGES * (DM_BC + DM_BN) * DM_S;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+  const uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+  const int bytes = valid ? 16 : 0;  // src-size 0 => zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 2) gwb_synth_dmma_kernel(double* __restrict__ G, const double* __restrict__ A,
+                                                                 int64_t lda, const double* __restrict__ Z, int npts,
+                                                                 int J, int64_t ncols, int lower_tri, int c_tiles,
+                                                                 int n_tiles) {
+  extern __shared__ __align__(16) double dm_smem[];
+  double* Zs = dm_smem;                                   // [STAGES][128][20]
+  double* As = dm_smem + size_t(DM_STAGES) * DM_BC * DM_S;  // [STAGES][64][20]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nt = n_tiles - 1 - int(blockIdx.x / c_tiles);  // heavy (large n0) tiles first
+  const int ct = blockIdx.x % c_tiles;
+  const int n0 = nt * DM_BN;
+  const int64_t c0 = int64_t(ct) * DM_BC;
+  const int kend = lower_tri ? min(J, n0 + DM_BN) : J;
+  const int nk = (kend + DM_BK - 1) / DM_BK;
+  const int wc = (warp & 3) * 32, wn = (warp >> 2) * 32;
+  const int fr = lane >> 2, fk = lane & 3;
+
+  auto load_stage = [&](int kt, int st) {
+    const int k0 = kt * DM_BK;
+    // Z: 128 rows x 8 chunks ; A: 64 rows x 8 chunks (chunk = 2 doubles)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int ch = tid + i * 256;
+      const int row = ch >> 3, kc = (ch & 7) * 2;
+      const int64_t c = c0 + row;
+      const bool ok = (c < ncols) && (k0 + kc < J);
+      cp_async16(Zs + (size_t(st) * DM_BC + row) * DM_S + kc, Z + (ok ? size_t(c) * J + k0 + kc : 0), ok);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int ch = tid + i * 256;
+      const int row = ch >> 3, kc = (ch & 7) * 2;
+      const int n = n0 + row;
+      const bool ok = (n < npts) && (k0 + kc < J);
+      cp_async16(As + (size_t(st) * DM_BN + row) * DM_S + kc, A + (ok ? size_t(n) * lda + k0 + kc : 0), ok);
+    }
+  };
+
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int m = 0; m < 4; ++m) acc[i][m][0] = acc[i][m][1] = 0.0;
+
+#pragma unroll
+  for (int s = 0; s < DM_STAGES - 1; ++s) {
+    if (s < nk) load_stage(s, s);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int kt = 0; kt < nk; ++kt) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(DM_STAGES - 2) : "memory");
+    __syncthreads();
+    {  // prefetch tile kt + STAGES - 1 into the slot freed in the previous iteration
+      const int nxt = kt + DM_STAGES - 1;
+      if (nxt < nk) load_stage(nxt, nxt % DM_STAGES);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    const int st = kt % DM_STAGES;
+    const double* zs = Zs + size_t(st) * DM_BC * DM_S;
+    const double* as = As + size_t(st) * DM_BN * DM_S;
+#pragma unroll
+    for (int kk = 0; kk < DM_BK; kk += 4) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = zs[(wc + i * 8 + fr) * DM_S + kk + fk];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) b[m] = as[(wn + m * 8 + fr) * DM_S + kk + fk];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(acc[i][m][0]), "+d"(acc[i][m][1])
+                       : "d"(a[i]), "d"(b[m]));
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  const bool vec_ok = (npts & 1) == 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t c = c0 + wc + i * 8 + fr;
+    if (c >= ncols) continue;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int n = n0 + wn + m * 8 + 2 * fk;
+      double* g = G + size_t(c) * npts + n;
+      if (vec_ok && n + 1 < npts) {
+        *reinterpret_cast<double2*>(g) = make_double2(acc[i][m][0], acc[i][m][1]);
+      } else {
+        if (n < npts) g[0] = acc[i][m][0];
+        if (n + 1 < npts) g[1] = acc[i][m][1];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Lower Cholesky, one CTA per matrix, left-looking; every inner product is a warp-shuffle
 // reduction (north_star: "warp-shuffle reductions for the small dense Cholesky").
 __device__ __forceinline__ double warp_sum(double v) {
