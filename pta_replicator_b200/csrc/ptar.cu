@@ -97,18 +97,18 @@ __global__ void philox_normals_kernel(float* __restrict__ out, int kind, int psr
   out[k] = z[realization & 3];
 }
 
-template <int RC, bool INJECT>
+template <int RC, bool INJECT, int WHITE, int DET>
 int launch_gen(const ptar_gen_params& p, cudaStream_t st) {
   const size_t smem = ptar::gen_smem_bytes(p.J, RC);
   if (smem > 227 * 1024) return fail(-3, "ptar_generate: J too large for shared memory%s");
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
-    cudaFuncSetAttribute(ptar::gen_kernel<RC, INJECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(ptar::gen_kernel<RC, INJECT, WHITE, DET>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
   const dim3 grid((p.nreal + RC - 1) / RC, p.n_tiles);
   if (grid.y > 65535) return fail(-3, "ptar_generate: more than 65535 tiles%s");
-  ptar::gen_kernel<RC, INJECT><<<grid, ptar::GEN_THREADS, smem, st>>>(p, ptar::philox_keys(p.seed));
+  ptar::gen_kernel<RC, INJECT, WHITE, DET><<<grid, ptar::GEN_THREADS, smem, st>>>(p, ptar::philox_keys(p.seed));
   return check_launch("ptar_generate");
 }
 
@@ -151,12 +151,26 @@ int ptar_gwb_mix(double* Zm, const double* M, const double* zin, int n_psr, int 
                  int64_t real0, void* stream) {
   if (!Zm || !M || n_psr <= 0 || J <= 0 || nreal <= 0) return fail(-1, "ptar_gwb_mix: bad argument%s");
   if (!zin && (real0 & 3)) return fail(-2, "ptar_gwb_mix: real0 must be a multiple of 4%s");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const dim3 grid((J + ptar::MIX_JT - 1) / ptar::MIX_JT, static_cast<unsigned>((nreal + 3) / 4));
+  static const bool use_fma = getenv("PTAR_MIX_FMA") != nullptr;  // legacy FMA-pipe kernel, kept for A/B runs
+  if (!use_fma) {
+    const int KP = (n_psr + 3) & ~3, NP = (n_psr + 7) & ~7;
+    const size_t smem = sizeof(double) * (size_t(KP) * ptar::MX_ZS + size_t(NP) * (KP + 4));
+    if (smem > 227 * 1024) return fail(-3, "ptar_gwb_mix: too many pulsars for shared memory%s");
+    if (zin) {
+      cudaFuncSetAttribute(ptar::gwb_mix_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      ptar::gwb_mix_dmma_kernel<true><<<grid, 256, smem, st>>>(Zm, M, zin, n_psr, J, nreal, ptar::philox_keys(seed), real0);
+    } else {
+      cudaFuncSetAttribute(ptar::gwb_mix_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      ptar::gwb_mix_dmma_kernel<false><<<grid, 256, smem, st>>>(Zm, M, zin, n_psr, J, nreal, ptar::philox_keys(seed), real0);
+    }
+    return check_launch("ptar_gwb_mix");
+  }
   const size_t smem = sizeof(double) * size_t(n_psr) * ptar::MIX_JT * 4;
   if (smem > 227 * 1024) return fail(-3, "ptar_gwb_mix: too many pulsars for shared memory%s");
   const int nwarps = (n_psr + 3) / 4;
   const int threads = 32 * (nwarps < 4 ? 4 : (nwarps > 32 ? 32 : nwarps));
-  const dim3 grid((J + ptar::MIX_JT - 1) / ptar::MIX_JT, static_cast<unsigned>((nreal + 3) / 4));
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (zin) {
     cudaFuncSetAttribute(ptar::gwb_mix_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     ptar::gwb_mix_kernel<true><<<grid, threads, smem, st>>>(Zm, M, zin, n_psr, J, nreal, seed, real0);
@@ -215,8 +229,18 @@ int ptar_generate(const ptar_gen_params* pp, void* stream) {
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int rc = p.rc ? p.rc : 16;
-  if (rc == 16) return inject ? launch_gen<16, true>(p, st) : launch_gen<16, false>(p, st);
-  return fail(-2, "ptar_generate: rc must be 16%s");
+  if (rc != 16) return fail(-2, "ptar_generate: rc must be 16%s");
+  if (inject) return launch_gen<16, true, -1, -1>(p, st);
+  const int white = !(p.flags & PTAR_F_WHITE) ? 0 : ((p.flags & PTAR_F_WHITE1) ? 1 : 2);
+  const bool det = (p.flags & PTAR_F_DET) != 0;
+  switch (white * 2 + (det ? 1 : 0)) {
+    case 0: return launch_gen<16, false, 0, 0>(p, st);
+    case 1: return launch_gen<16, false, 0, 1>(p, st);
+    case 2: return launch_gen<16, false, 1, 0>(p, st);
+    case 3: return launch_gen<16, false, 1, 1>(p, st);
+    case 4: return launch_gen<16, false, 2, 0>(p, st);
+    default: return launch_gen<16, false, 2, 1>(p, st);
+  }
 }
 
 int ptar_philox_normals(float* out, int kind, int psr, int64_t realization, int64_t idx0, int64_t n, uint64_t seed,

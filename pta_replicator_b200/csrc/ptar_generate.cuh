@@ -50,7 +50,10 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
-template <int RC, bool INJECT>
+// WHITE / DET: -1 = decided at run time from P.flags (generic build, used by the parity mode);
+// WHITE 0/1/2 = no white noise / one merged draw / two draws, DET 0/1 = no / with deterministic term
+// (specialised builds of the throughput mode: the flag tests disappear from the inner loop).
+template <int RC, bool INJECT, int WHITE, int DET>
 __global__ void __launch_bounds__(GEN_THREADS, GEN_MIN_CTAS) gen_kernel(const ptar_gen_params P, const PhiloxKeys K) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
@@ -210,9 +213,9 @@ __global__ void __launch_bounds__(GEN_THREADS, GEN_MIN_CTAS) gen_kernel(const pt
   }
 
   // ---- TOA stage ---------------------------------------------------------------------
-  const bool has_white = (flags & PTAR_F_WHITE) != 0;
-  const bool two_draws = has_white && !(flags & PTAR_F_WHITE1);
-  const bool has_det = (flags & PTAR_F_DET) != 0;
+  const bool has_white = WHITE >= 0 ? (WHITE > 0) : ((flags & PTAR_F_WHITE) != 0);
+  const bool two_draws = WHITE >= 0 ? (WHITE == 2) : (has_white && !(flags & PTAR_F_WHITE1));
+  const bool has_det = DET >= 0 ? (DET > 0) : ((flags & PTAR_F_DET) != 0);
   const size_t ld = static_cast<size_t>(P.ld_out);
   for (int tt = tid; tt < tile.n_toa; tt += GEN_THREADS) {
     const size_t gi = size_t(tile.toa_start) + tt;
@@ -226,7 +229,10 @@ __global__ void __launch_bounds__(GEN_THREADS, GEN_MIN_CTAS) gen_kernel(const pt
     double* orow = P.out + size_t(r0) * ld + gi;
 #pragma unroll 1
     for (int rg = 0; rg * 4 < nr; ++rg, orow += 4 * ld) {
-      float n1[4] = {0.f, 0.f, 0.f, 0.f}, n2[4] = {0.f, 0.f, 0.f, 0.f};
+      float n1[4], n2[4];
+      if (INJECT) {
+        n1[0] = n1[1] = n1[2] = n1[3] = n2[0] = n2[1] = n2[2] = n2[3] = 0.f;
+      }
       if (!INJECT && has_white) {
         normals4(n1, wblock, PTAR_K_WHITE1, psr, rgroup0 + rg, K);
         if (two_draws) normals4(n2, wblock, PTAR_K_WHITE2, psr, rgroup0 + rg, K);

@@ -89,6 +89,79 @@ __global__ void __launch_bounds__(1024) gwb_mix_kernel(double* __restrict__ Zm, 
 }
 
 // ---------------------------------------------------------------------------------------
+// ORF mixing on the fp64 tensor path.  Per CTA: 32 grid columns x 4 realizations = 128 rows
+// (row = l*32 + jj), D[row][p] = sum_q z[q][row] * M[p][q]; K = q padded to a multiple of 4,
+// N = p padded to a multiple of 8.  Draws z (Philox or injected) are staged in shared memory as
+// zs[q][row] (row stride 132 -> the 8x4 A-fragment gather is conflict free), M as ms[p][q] (row
+// stride KP+4).  Warp w owns rows 16w..16w+15 (2 m-tiles) and all n-tiles; k-steps beyond an
+// n-tile's last pulsar are skipped (M is lower triangular).
+constexpr int MX_ROWS = 128, MX_ZS = MX_ROWS + 4;
+
+template <bool INJECT>
+__global__ void __launch_bounds__(256) gwb_mix_dmma_kernel(double* __restrict__ Zm, const double* __restrict__ M,
+                                                            const double* __restrict__ zin, int P, int J,
+                                                            int64_t nreal, const PhiloxKeys K, int64_t real0) {
+  extern __shared__ __align__(16) double mx_smem[];
+  const int KP = (P + 3) & ~3, NP = (P + 7) & ~7, MS = KP + 4;
+  double* zs = mx_smem;                      // [KP][132]
+  double* ms = mx_smem + size_t(KP) * MX_ZS;  // [NP][MS]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int j0 = blockIdx.x * MIX_JT;
+  const int64_t rbase = int64_t(blockIdx.y) * 4;
+  for (int idx = tid; idx < NP * MS; idx += 256) {
+    const int p = idx / MS, q = idx % MS;
+    ms[idx] = (p < P && q <= p) ? __ldg(M + size_t(p) * P + q) : 0.0;
+  }
+  for (int idx = tid; idx < KP * MIX_JT; idx += 256) {
+    const int q = idx / MIX_JT, jj = idx % MIX_JT, j = j0 + jj;
+    double z[4] = {0, 0, 0, 0};
+    if (q < P && j < J) {
+      if (INJECT) {
+#pragma unroll
+        for (int l = 0; l < 4; ++l)
+          if (rbase + l < nreal) z[l] = zin[((rbase + l) * P + q) * J + j];
+      } else {
+        float n[4];
+        normals4(n, j, PTAR_K_GWB, q, static_cast<uint64_t>(real0 + rbase) >> 2, K);
+#pragma unroll
+        for (int l = 0; l < 4; ++l) z[l] = static_cast<double>(n[l]);
+      }
+    }
+#pragma unroll
+    for (int l = 0; l < 4; ++l) zs[size_t(q) * MX_ZS + l * MIX_JT + jj] = z[l];
+  }
+  __syncthreads();
+  const int fr = lane >> 2, fk = lane & 3;
+  const int row0 = warp * 16;
+  const int n_nt = NP / 8;
+  for (int nt = 0; nt < n_nt; ++nt) {
+    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    const int kmax = min(KP, (nt * 8 + 8 + 3) & ~3);  // q <= p < nt*8+8
+    for (int k0 = 0; k0 < kmax; k0 += 4) {
+      const double b = ms[(nt * 8 + fr) * MS + k0 + fk];
+      const double a0 = zs[size_t(k0 + fk) * MX_ZS + row0 + fr];
+      const double a1 = zs[size_t(k0 + fk) * MX_ZS + row0 + 8 + fr];
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(acc[0][0]), "+d"(acc[0][1]) : "d"(a0), "d"(b));
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(acc[1][0]), "+d"(acc[1][1]) : "d"(a1), "d"(b));
+    }
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int row = row0 + t * 8 + fr;
+      const int l = row >> 5, jj = row & 31, j = j0 + jj;
+      if (j < J && rbase + l < nreal) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int p = nt * 8 + 2 * fk + u;
+          if (p < P) Zm[((rbase + l) * P + p) * J + j] = acc[t][u];
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // G[c][n] = sum_j A[n][j] * Z[c][j]   (both operands K-contiguous; fp64 FMA pipe)
 // 64x64 tile, BK = 16, 256 threads, 4x4 register micro-tile, register-prefetched next tile.
 constexpr int SY_BM = 64, SY_BN = 64, SY_BK = 16, SY_PAD = 2;
