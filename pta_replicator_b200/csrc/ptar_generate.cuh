@@ -36,6 +36,10 @@ constexpr int GEN_THREADS = 256;
 #define GEN_MIN_CTAS 3
 #endif
 constexpr int EP = PTAR_TILE_EPOCHS;  // 64
+#ifndef GEN_UNROLL
+#define GEN_UNROLL 1
+#endif
+constexpr int kGenUnroll = GEN_UNROLL;
 
 __host__ __device__ constexpr int gen_css(int RC) { return 3 * RC + 2; }  // even (16-B rows), 4e-word bank skew
 
@@ -78,10 +82,16 @@ __global__ void __launch_bounds__(GEN_THREADS, GEN_MIN_CTAS) gen_kernel(const pt
   const uint64_t rgroup0 = static_cast<uint64_t>(P.real0 + r0) >> 2;
 
   // ---- epoch stage -------------------------------------------------------------------
-  // GEMM ownership: thread -> realization rr, epochs e0..e0+3
+  // GEMM ownership: thread -> realization rr, epochs e0..e0+3, slice ks of the J columns.  Tiles with
+  // few epochs split the column range 2- or 4-way so that all 8 warps work (split-K, reduced through
+  // shared memory below).
   static_assert(RC == 16, "thread -> (realization, 4 epochs) ownership below assumes RC == 16");
-  const int rr = tid & 15;
-  const int e0 = (tid >> 4) * 4;
+  const int nsplit = tile.n_ep <= 16 ? 4 : (tile.n_ep <= 32 ? 2 : 1);
+  const int eper = EP / nsplit;                 // epochs covered per split group
+  const int gthreads = GEN_THREADS / nsplit;    // threads per split group
+  const int ks = tid / gthreads, tg = tid % gthreads;
+  const int rr = tg & 15;
+  const int e0 = (tg >> 4) * 4;
   double acc[4][3];
 #pragma unroll
   for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = 0.0;
@@ -103,36 +113,54 @@ __global__ void __launch_bounds__(GEN_THREADS, GEN_MIN_CTAS) gen_kernel(const pt
           "l"(src), "r"(bytes), "r"(smem_u32(mbar))
           : "memory");
     }
-    // coefficients a = sqrt(prior) * z for RC realizations (overlaps the bulk copy)
-    const double* scale = P.rn_scale + size_t(psr) * J;
-    if (INJECT) {
-      for (int idx = tid; idx < J * RC; idx += GEN_THREADS) {
-        const int j = idx / RC, r = idx % RC;
-        As[idx] = (r < nr) ? scale[j] * P.zrn[(size_t(r0 + r) * P.n_psr + psr) * J + j] : 0.0;
-      }
-    } else {
-      for (int idx = tid; idx < J * RG; idx += GEN_THREADS) {
-        const int j = idx / RG, rg = idx % RG;
-        float n[4];
-        normals4(n, j, PTAR_K_RED, psr, rgroup0 + rg, K);
-        const double s = scale[j];
+    // coefficients a = sqrt(prior) * z for RC realizations and their first two time derivatives
+    // (1/2 folded into the 2nd); one work item = one (cos, sin) column pair x 4 realizations.
+    // Overlaps the bulk copy.
+    {
+      const double* scale = P.rn_scale + size_t(psr) * J;
+      const double* om = P.rn_omega + size_t(psr) * (J / 2);
+      const double sgn_even = P.rn_convention ? 1.0 : -1.0;
+      double* A0 = As;
+      double* A1 = As + size_t(J) * RC;
+      double* A2 = As + size_t(2) * J * RC;
+      for (int idx = tid; idx < (J / 2) * RG; idx += GEN_THREADS) {
+        const int k = idx / RG, rg = idx % RG;
+        const int je = 2 * k, jo = 2 * k + 1;
+        double ye[4], yo[4];
+        if (INJECT) {
 #pragma unroll
-        for (int l = 0; l < 4; ++l) As[j * RC + rg * 4 + l] = s * static_cast<double>(n[l]);
+          for (int l = 0; l < 4; ++l) {
+            const int r = rg * 4 + l;
+            const bool ok = r < nr;
+            const size_t zi = (size_t(r0 + (ok ? r : 0)) * P.n_psr + psr) * J;
+            ye[l] = ok ? P.zrn[zi + je] : 0.0;
+            yo[l] = ok ? P.zrn[zi + jo] : 0.0;
+          }
+        } else {
+          float n[4];
+          normals4(n, je, PTAR_K_RED, psr, rgroup0 + rg, K);
+#pragma unroll
+          for (int l = 0; l < 4; ++l) ye[l] = static_cast<double>(n[l]);
+          normals4(n, jo, PTAR_K_RED, psr, rgroup0 + rg, K);
+#pragma unroll
+          for (int l = 0; l < 4; ++l) yo[l] = static_cast<double>(n[l]);
+        }
+        const double se = scale[je], so = scale[jo], w = om[k];
+        const double h = -0.5 * w * w;
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+          const int c = rg * 4 + l;
+          const double a_e = se * ye[l], a_o = so * yo[l];
+          A0[je * RC + c] = a_e;
+          A0[jo * RC + c] = a_o;
+          A1[je * RC + c] = sgn_even * w * a_o;
+          A1[jo * RC + c] = -sgn_even * w * a_e;
+          A2[je * RC + c] = h * a_e;
+          A2[jo * RC + c] = h * a_o;
+        }
       }
     }
     __syncthreads();
-    if (nd > 1) {  // time derivatives of the coefficient vector (1/2 folded into the 2nd)
-      const double* om = P.rn_omega + size_t(psr) * (J / 2);
-      const double sgn_even = P.rn_convention ? 1.0 : -1.0;
-      for (int idx = tid; idx < J * RC; idx += GEN_THREADS) {
-        const int j = idx / RC, r = idx % RC;
-        const double w = om[j >> 1];
-        const double partner = As[(j ^ 1) * RC + r];
-        As[J * RC + idx] = ((j & 1) ? -sgn_even : sgn_even) * w * partner;
-        As[2 * J * RC + idx] = -0.5 * w * w * As[idx];
-      }
-      __syncthreads();
-    }
     {  // wait for the basis tile
       uint32_t done = 0;
       while (!done) {
@@ -145,9 +173,10 @@ __global__ void __launch_bounds__(GEN_THREADS, GEN_MIN_CTAS) gen_kernel(const pt
             : "memory");
       }
     }
-    // C[e][r][d] = sum_j F[j][e] * A[d][j][r]
+    // C[e][r][d] = sum_j F[j][e] * A[d][j][r]   (this thread: columns [jlo, jhi))
     if (e0 < tile.n_ep) {
-      for (int j = 0; j < J; ++j) {
+      const int jlo = (J * ks) / nsplit, jhi = (J * (ks + 1)) / nsplit;
+      for (int j = jlo; j < jhi; ++j) {
         const double2 f01 = *reinterpret_cast<const double2*>(Fs + j * EP + e0);
         const double2 f23 = *reinterpret_cast<const double2*>(Fs + j * EP + e0 + 2);
         const double f[4] = {f01.x, f01.y, f23.x, f23.y};
@@ -162,23 +191,28 @@ __global__ void __launch_bounds__(GEN_THREADS, GEN_MIN_CTAS) gen_kernel(const pt
       }
     }
     __syncthreads();  // everyone is done reading Fs / As: Cs may overwrite them
-  }
-  if (has_epoch) {
-    // GWB grid interpolation at the epoch reference time and its slope (exactly linear inside the epoch)
-    if (has_gwb && rr < nr) {
-      const double* Gr = P.G + (size_t(r0 + rr) * P.n_psr + psr) * P.npts;
+    if (nsplit > 1) {  // split-K reduction: groups ks >= 1 park their partial sums in rows ks*eper + e
+      if (ks > 0) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int e = e0 + i;
-        if (e < tile.n_ep) {
-          const int ge = tile.ep_start + e;
-          const int j = P.ep_gidx[ge];
-          const double g0 = __ldg(Gr + j), dg = __ldg(Gr + j + 1) - g0;
-          acc[i][0] += fma(P.ep_gw[ge], dg, g0);
-          acc[i][1] += dg * P.ep_ginv[ge];
+        for (int i = 0; i < 4; ++i) {
+          double* c = Cs + (ks * eper + e0 + i) * CSS + rr * 3;
+          c[0] = acc[i][0]; c[1] = acc[i][1]; c[2] = acc[i][2];
         }
       }
+      __syncthreads();
+      if (ks == 0) {
+        for (int g = 1; g < nsplit; ++g) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const double* c = Cs + (g * eper + e0 + i) * CSS + rr * 3;
+            acc[i][0] += c[0]; acc[i][1] += c[1]; acc[i][2] += c[2];
+          }
+        }
+      }
+      __syncthreads();
     }
+  }
+  if (has_epoch && ks == 0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       double* c = Cs + (e0 + i) * CSS + rr * 3;
@@ -186,31 +220,52 @@ __global__ void __launch_bounds__(GEN_THREADS, GEN_MIN_CTAS) gen_kernel(const pt
       c[1] = acc[i][1];
       c[2] = acc[i][2];
     }
+  }
+  if (has_epoch && (has_ecorr || has_gwb)) {
     __syncthreads();
-    if (has_ecorr) {
-      if (INJECT) {
-        for (int idx = tid; idx < tile.n_ep * RC; idx += GEN_THREADS) {
-          const int e = idx / RC, r = idx % RC;
+    // one pass over (epoch, 4 realizations): ECORR draw of the epoch's bucket, and the GWB grid
+    // interpolation at the epoch reference time with its slope (exactly linear inside the epoch)
+    for (int idx = tid; idx < tile.n_ep * RG; idx += GEN_THREADS) {
+      const int e = idx / RG, rg = idx % RG;
+      const int ge = tile.ep_start + e;
+      double add0[4] = {0.0, 0.0, 0.0, 0.0}, add1[4] = {0.0, 0.0, 0.0, 0.0};
+      if (has_gwb) {
+        const int j = P.ep_gidx[ge];
+        const double gwt = P.ep_gw[ge], ginv = P.ep_ginv[ge];
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+          const int r = rg * 4 + l;
           if (r < nr) {
-            const int ge = tile.ep_start + e;
-            Cs[e * CSS + r * 3] +=
-                P.ep_ecorr[ge] * P.zb[size_t(r0 + r) * P.n_bucket_total + P.psr_bucket_off[psr] + P.ep_bucket[ge]];
+            const double* Gr = P.G + (size_t(r0 + r) * P.n_psr + psr) * P.npts + j;
+            const double g0 = __ldg(Gr), dg = __ldg(Gr + 1) - g0;
+            add0[l] = fma(gwt, dg, g0);
+            add1[l] = dg * ginv;
           }
         }
-      } else {
-        for (int idx = tid; idx < tile.n_ep * RG; idx += GEN_THREADS) {
-          const int e = idx / RG, rg = idx % RG;
-          const int ge = tile.ep_start + e;
-          const double ec = P.ep_ecorr[ge];
+      }
+      if (has_ecorr) {
+        const double ec = P.ep_ecorr[ge];
+        if (INJECT) {
+          const size_t zo = P.psr_bucket_off[psr] + P.ep_bucket[ge];
+#pragma unroll
+          for (int l = 0; l < 4; ++l)
+            if (rg * 4 + l < nr) add0[l] += ec * P.zb[size_t(r0 + rg * 4 + l) * P.n_bucket_total + zo];
+        } else {
           float n[4];
           normals4(n, P.ep_bucket[ge], PTAR_K_ECORR, psr, rgroup0 + rg, K);
 #pragma unroll
-          for (int l = 0; l < 4; ++l) Cs[e * CSS + (rg * 4 + l) * 3] += ec * static_cast<double>(n[l]);
+          for (int l = 0; l < 4; ++l) add0[l] += ec * static_cast<double>(n[l]);
         }
       }
-      __syncthreads();
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        double* c = Cs + e * CSS + (rg * 4 + l) * 3;
+        c[0] += add0[l];
+        c[1] += add1[l];
+      }
     }
   }
+  if (has_epoch) __syncthreads();
 
   // ---- TOA stage ---------------------------------------------------------------------
   const bool has_white = WHITE >= 0 ? (WHITE > 0) : ((flags & PTAR_F_WHITE) != 0);
@@ -227,7 +282,7 @@ __global__ void __launch_bounds__(GEN_THREADS, GEN_MIN_CTAS) gen_kernel(const pt
     const int el = has_epoch ? static_cast<int>(P.eloc[gi]) : 0;
     const uint32_t wblock = static_cast<uint32_t>(tile.toa_local0 + tt);
     double* orow = P.out + size_t(r0) * ld + gi;
-#pragma unroll 1
+#pragma unroll kGenUnroll
     for (int rg = 0; rg * 4 < nr; ++rg, orow += 4 * ld) {
       float n1[4], n2[4];
       if (INJECT) {
@@ -265,12 +320,21 @@ __global__ void __launch_bounds__(GEN_THREADS, GEN_MIN_CTAS) gen_kernel(const pt
             }
           }
         } else {
+#ifdef GEN_WHITE_FP32
+          const float w1f = static_cast<float>(w1), w2f = static_cast<float>(w2);
+#pragma unroll
+          for (int l = 0; l < 4; ++l) {
+            const float x = two_draws ? fmaf(w2f, n2[l], w1f * n1[l]) : w1f * n1[l];
+            v[l] += static_cast<double>(x);
+          }
+#else
 #pragma unroll
           for (int l = 0; l < 4; ++l) v[l] = fma(w1, static_cast<double>(n1[l]), v[l]);
           if (two_draws) {
 #pragma unroll
             for (int l = 0; l < 4; ++l) v[l] = fma(w2, static_cast<double>(n2[l]), v[l]);
           }
+#endif
         }
       }
       if (rg * 4 + 4 <= nr) {  // streaming stores: the output is never re-read by this kernel

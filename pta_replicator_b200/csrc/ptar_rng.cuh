@@ -25,9 +25,12 @@ __host__ __device__ inline PhiloxKeys philox_keys(uint64_t seed) {
   return K;
 }
 
+#ifndef PHILOX_ROUNDS
+#define PHILOX_ROUNDS 10
+#endif
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKeys& K) {
 #pragma unroll
-  for (int i = 0; i < 10; ++i) {
+  for (int i = 0; i < PHILOX_ROUNDS; ++i) {
     const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * c.x;
     const uint64_t p1 = static_cast<uint64_t>(0xCD9E8D57u) * c.z;
     c = make_uint4(static_cast<uint32_t>(p1 >> 32) ^ c.y ^ K.k0[i], static_cast<uint32_t>(p1),
