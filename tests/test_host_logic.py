@@ -184,6 +184,20 @@ def test_orf_l0_matches_reference_fixture():
     assert abs(ra - np.pi / 2) < 1e-12 and abs(dec - np.radians(23.4392911)) < 1e-12
 
 
+def test_orf_anisotropic_basis_matches_reference_fixture():
+    """lmax = 6 on 9 pulsars incl. a coincident and an antipodal pair, against the reference's own
+    ``correlated_basis`` (tests/golden/ref_orf.npz).  The computational-frame sums alternate with
+    factorial-sized terms; for one close pair the reference's own rounding noise is ~2e-11."""
+    from pta_replicator_b200 import orf
+    z = np.load(os.path.join(GOLD, "ref_orf.npz"))
+    got = np.array(orf.correlated_basis(z["locs"], 6))
+    assert got.shape == (49, 9, 9)
+    assert np.max(np.abs(got - z["basis_l6"])) < 1e-10
+    assert np.median(np.abs(got - z["basis_l6"])) < 1e-15
+    for k in range(49):
+        assert np.array_equal(got[k], got[k].T)
+
+
 def test_shard_bounds_cover_everything():
     from pta_replicator_b200.distributed import shard_bounds
     for nreal in (0, 1, 3, 4, 1000, 100000, 1003):
