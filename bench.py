@@ -129,6 +129,8 @@ def main():
     ap.add_argument("--e2e-nreal", type=int, default=256)
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="serialize GWB-grid and generator kernels on one stream")
     ap.add_argument("--gather", action="store_true", help="also time an NCCL all-gather of one chunk of residuals")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -157,6 +159,7 @@ def main():
     synthetic.ng15_recipe(b, noise)
     if args.chunk:
         b.default_chunk = args.chunk
+    b.overlap_gwb = not args.no_overlap
     st = b.compile()
     R = args.nreal
     out = torch.empty((R, b.ld), dtype=torch.float64, device=b.device)
@@ -168,26 +171,30 @@ def main():
         real0 = ((k * world + rank) * R + 3) // 4 * 4
         b.generate(R, seed=seed, real0=real0, out=out, rc=args.rc, timers=timers)
 
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()          # samples span warm-up + timed region (both are the same load)
+        time.sleep(0.3)
     for k in range(args.warmup):
         step(k)
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
-        time.sleep(0.25)
-    timers = {}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
     for k in range(args.steps):
-        step(args.warmup + k, timers)
+        step(args.warmup + k)            # product schedule (GWB grid of chunk c+1 overlaps generate(c))
     e1.record()
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
     ms = e0.elapsed_time(e1)
+    # per-kernel durations: the same K steps again, serialized on one stream with CUDA events around every launch
+    timers = {}
+    for k in range(args.steps):
+        step(args.warmup + args.steps + k, timers)
+    torch.cuda.synchronize()
     clocks = sampler.finish() if sampler else None
     tms = torch.tensor([ms], dtype=torch.float64, device=b.device)
     if dist is not None:
@@ -223,8 +230,35 @@ def main():
                        "white_draws_per_toa": 1 if args.merged_white else 2, "gwb_chunk": chunk_real,
                        "l2": f"output per step {R * b.ld * 8 / 1e9:.2f} GB > L2 (126 MB); no flush needed",
                        "parallelism": f"realization-sharded x{world}, no data-path collective"},
-            "kernels": kern, "roofline": roof, "clocks": clocks,
+            "kernels": kern, "kernels_timing": "second pass of the same K steps, serialized on one stream, CUDA events around every launch "
+                                               "(the timed region overlaps gwb_mix/gwb_synth of chunk c+1 with generate of chunk c on two streams"
+                                               + ("" if b.overlap_gwb else " -- DISABLED by --no-overlap") + ")",
+            "roofline": roof, "clocks": clocks,
             "gpu_launches": int(sum(k["launches"] for k in kern.values()))}
+
+    # ---- variant: one merged white draw per TOA (identical distribution; PTAR_F_WHITE1), rank 0, N == 1 only
+    if world == 1 and not args.merged_white and not args.no_variants:
+        b1 = PulsarBatch(psrs)
+        b1.white_merged = True
+        synthetic.ng15_recipe(b1, noise)
+        if args.chunk:
+            b1.default_chunk = args.chunk
+        for k in range(2):
+            b1.generate(R, seed=seed, real0=0, out=out, rc=args.rc)
+        tv = {}
+        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        v0.record()
+        for k in range(3):
+            b1.generate(R, seed=seed, real0=4 * R * (k + 1), out=out, rc=args.rc, timers=tv)
+        v1.record()
+        torch.cuda.synchronize()
+        gv = [a.elapsed_time(z) for n, a, z in tv["events"] if n == "generate"]
+        line["variants"] = {"merged_white_draw": {
+            "value": 3 * R / (v0.elapsed_time(v1) * 1e-3), "unit": "realizations/s",
+            "roofline_frac": 8.0 * b.n_toa_total * (3 * R / len(gv)) / (float(np.mean(gv)) * 1e-3) / 1e9 / hbm,
+            "note": "w1 z1 + w2 z2 replaced by sqrt(w1^2+w2^2) z: same Gaussian law, one Philox draw per TOA; not the headline"}}
+        del b1
 
     # ---- e2e through the C ABI with host buffers (rank-local; aggregated like `value`)
     Re = min(args.e2e_nreal, R)

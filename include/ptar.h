@@ -108,7 +108,7 @@ typedef struct {
   double* out;
   int64_t ld_out;
   int32_t nreal;
-  int32_t rc;         /* realizations per CTA: 16 (0 = default)                          */
+  int32_t rc;         /* realizations per CTA: 16 (256 threads) or 32 (512 threads); 0 = default */
 } ptar_gen_params;
 
 int         ptar_version(void);

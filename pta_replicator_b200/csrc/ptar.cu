@@ -108,7 +108,7 @@ int launch_gen(const ptar_gen_params& p, cudaStream_t st) {
   }
   const dim3 grid((p.nreal + RC - 1) / RC, p.n_tiles);
   if (grid.y > 65535) return fail(-3, "ptar_generate: more than 65535 tiles%s");
-  ptar::gen_kernel<RC, INJECT, WHITE, DET><<<grid, ptar::GEN_THREADS, smem, st>>>(p, ptar::philox_keys(p.seed));
+  ptar::gen_kernel<RC, INJECT, WHITE, DET><<<grid, ptar::gen_threads(RC), smem, st>>>(p, ptar::philox_keys(p.seed));
   return check_launch("ptar_generate");
 }
 
@@ -229,10 +229,20 @@ int ptar_generate(const ptar_gen_params* pp, void* stream) {
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int rc = p.rc ? p.rc : 16;
-  if (rc != 16) return fail(-2, "ptar_generate: rc must be 16%s");
+  if (rc != 16 && rc != 32) return fail(-2, "ptar_generate: rc must be 16 or 32%s");
   if (inject) return launch_gen<16, true, -1, -1>(p, st);
   const int white = !(p.flags & PTAR_F_WHITE) ? 0 : ((p.flags & PTAR_F_WHITE1) ? 1 : 2);
   const bool det = (p.flags & PTAR_F_DET) != 0;
+  if (rc == 32) {
+    switch (white * 2 + (det ? 1 : 0)) {
+      case 0: return launch_gen<32, false, 0, 0>(p, st);
+      case 1: return launch_gen<32, false, 0, 1>(p, st);
+      case 2: return launch_gen<32, false, 1, 0>(p, st);
+      case 3: return launch_gen<32, false, 1, 1>(p, st);
+      case 4: return launch_gen<32, false, 2, 0>(p, st);
+      default: return launch_gen<32, false, 2, 1>(p, st);
+    }
+  }
   switch (white * 2 + (det ? 1 : 0)) {
     case 0: return launch_gen<16, false, 0, 0>(p, st);
     case 1: return launch_gen<16, false, 0, 1>(p, st);

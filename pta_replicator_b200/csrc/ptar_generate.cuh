@@ -31,10 +31,9 @@
 
 namespace ptar {
 
-constexpr int GEN_THREADS = 256;
-#ifndef GEN_MIN_CTAS
-#define GEN_MIN_CTAS 3
-#endif
+// A CTA has 16 threads per realization of its chunk: RC = 16 -> 256 threads (4 CTAs/SM),
+// RC = 32 -> 512 threads (2 CTAs/SM; the epoch stage is amortised over twice the outputs).
+__host__ __device__ constexpr int gen_threads(int RC) { return 16 * RC; }
 constexpr int EP = PTAR_TILE_EPOCHS;  // 64
 #ifndef GEN_UNROLL
 #define GEN_UNROLL 1
@@ -58,7 +57,8 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 // WHITE 0/1/2 = no white noise / one merged draw / two draws, DET 0/1 = no / with deterministic term
 // (specialised builds of the throughput mode: the flag tests disappear from the inner loop).
 template <int RC, bool INJECT, int WHITE, int DET>
-__global__ void __launch_bounds__(GEN_THREADS, GEN_MIN_CTAS) gen_kernel(const ptar_gen_params P, const PhiloxKeys K) {
+__global__ void __launch_bounds__(16 * RC, 1024 / (16 * RC)) gen_kernel(const ptar_gen_params P, const PhiloxKeys K) {
+  constexpr int GEN_THREADS = 16 * RC;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
   double* Fs = reinterpret_cast<double*>(smem_raw + 16);
@@ -85,13 +85,13 @@ __global__ void __launch_bounds__(GEN_THREADS, GEN_MIN_CTAS) gen_kernel(const pt
   // GEMM ownership: thread -> realization rr, epochs e0..e0+3, slice ks of the J columns.  Tiles with
   // few epochs split the column range 2- or 4-way so that all 8 warps work (split-K, reduced through
   // shared memory below).
-  static_assert(RC == 16, "thread -> (realization, 4 epochs) ownership below assumes RC == 16");
+  static_assert(RC == 16 || RC == 32, "RC must be 16 or 32");
   const int nsplit = tile.n_ep <= 16 ? 4 : (tile.n_ep <= 32 ? 2 : 1);
   const int eper = EP / nsplit;                 // epochs covered per split group
   const int gthreads = GEN_THREADS / nsplit;    // threads per split group
   const int ks = tid / gthreads, tg = tid % gthreads;
-  const int rr = tg & 15;
-  const int e0 = (tg >> 4) * 4;
+  const int rr = tg & (RC - 1);
+  const int e0 = (tg / RC) * 4;
   double acc[4][3];
 #pragma unroll
   for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = 0.0;

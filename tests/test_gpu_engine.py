@@ -160,6 +160,8 @@ def test_shards_and_chunks_are_bitwise_reproducible():
     assert torch.equal(full, d)
     e = b.generate(40, seed=4, real0=8)
     assert not torch.equal(full, e)
+    wide = b.generate(40, seed=3, real0=8, rc=32)          # 512-thread CTAs, 32 realizations each
+    assert torch.equal(full, wide)
     h = b.generate_to_host(40, seed=3, real0=8, chunk=16)
     assert torch.equal(full.cpu(), h)
 
