@@ -130,7 +130,6 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
-    ap.add_argument("--no-overlap", action="store_true", help="serialize GWB-grid and generator kernels on one stream")
     ap.add_argument("--gather", action="store_true", help="also time an NCCL all-gather of one chunk of residuals")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -159,7 +158,6 @@ def main():
     synthetic.ng15_recipe(b, noise)
     if args.chunk:
         b.default_chunk = args.chunk
-    b.overlap_gwb = not args.no_overlap
     st = b.compile()
     R = args.nreal
     out = torch.empty((R, b.ld), dtype=torch.float64, device=b.device)
@@ -184,7 +182,7 @@ def main():
     torch.cuda.synchronize()
     e0.record()
     for k in range(args.steps):
-        step(args.warmup + k)            # product schedule (GWB grid of chunk c+1 overlaps generate(c))
+        step(args.warmup + k)
     e1.record()
     torch.cuda.synchronize()
     if dist is not None:
@@ -230,9 +228,7 @@ def main():
                        "white_draws_per_toa": 1 if args.merged_white else 2, "gwb_chunk": chunk_real,
                        "l2": f"output per step {R * b.ld * 8 / 1e9:.2f} GB > L2 (126 MB); no flush needed",
                        "parallelism": f"realization-sharded x{world}, no data-path collective"},
-            "kernels": kern, "kernels_timing": "second pass of the same K steps, serialized on one stream, CUDA events around every launch "
-                                               "(the timed region overlaps gwb_mix/gwb_synth of chunk c+1 with generate of chunk c on two streams"
-                                               + ("" if b.overlap_gwb else " -- DISABLED by --no-overlap") + ")",
+            "kernels": kern, "kernels_timing": "second pass of the same K steps with CUDA events around every launch (same stream, same schedule)",
             "roofline": roof, "clocks": clocks,
             "gpu_launches": int(sum(k["launches"] for k in kern.values()))}
 

@@ -85,7 +85,7 @@ typedef struct {
   /* per-epoch statics (an epoch never straddles an ECORR bucket edge or a GWB grid knot) */
   const double*  ep_ecorr;   /* ecorr of the epoch's bucket [s]                          */
   const int32_t* ep_bucket;  /* ECORR bucket id within the pulsar                        */
-  const int32_t* ep_gidx;    /* GWB grid interval j of the epoch                         */
+  const int32_t* ep_gidx;    /* column of knot j in the compact grid G (knot j+1 is the next column) */
   const double*  ep_gw;      /* (t_ref - ut[j]) / (ut[j+1] - ut[j])                      */
   const double*  ep_ginv;    /* 1 / (ut[j+1] - ut[j])  [1/s]                             */
   const int64_t* psr_bucket_off; /* [n_psr]: offset of each pulsar in the injected zb axis */
@@ -93,8 +93,10 @@ typedef struct {
   /* per-pulsar red-noise statics */
   const double* rn_scale;    /* [n_psr][J] sqrt(prior)                                   */
   const double* rn_omega;    /* [n_psr][J/2] 2*pi*f_k                                    */
-  /* GWB grid for this batch of realizations: G[r][psr][npts] */
+  /* compact GWB grid for this batch of realizations: G[r][g_ld]; only the knots next to some TOA of a
+   * pulsar are present (ptar_gwb_synth) */
   const double* G;
+  int64_t g_ld;
   /* injected standard-normal draws (parity mode); all NULL => Philox */
   const double* z1;   /* [nreal][ld_out]                                                 */
   const double* z2;   /* [nreal][ld_out]                                                 */
@@ -131,15 +133,19 @@ int ptar_fourier_basis(double* out, const int64_t* row_off, int64_t col_stride,
 int ptar_cgw_delay(double* out, const double* t, const int32_t* psr_of_toa, const double* psr_par,
                    const double* src, int mode, int psr_term, int accumulate, int64_t n, void* stream);
 
-/* Zm[r][p][j] = sum_q M[p][q] z[r][q][j].  z is read from zin (parity) or drawn from Philox
- * (zin == NULL; stream PTAR_K_GWB).  M is n_psr x n_psr lower triangular, row-major. */
+/* Zm[p][r][j] = sum_q M[p][q] z[r][q][j]  (output pulsar-major: [n_psr][nreal][J]).  z is read from
+ * zin[r][q][j] (parity) or drawn from Philox (zin == NULL; stream PTAR_K_GWB).  M is n_psr x n_psr lower
+ * triangular, row-major. */
 int ptar_gwb_mix(double* Zm, const double* M, const double* zin, int n_psr, int J,
                  int64_t nreal, uint64_t seed, int64_t real0, void* stream);
 
-/* G[c][n] = sum_j A[n][j] * Zm[c][j],  n < npts, c < ncols (= nreal * n_psr).
- * lower_tri != 0 promises A[n][j] == 0 for j > n (skips those blocks). */
-int ptar_gwb_synth(double* G, const double* A, int64_t lda, const double* Zm, int npts, int J,
-                   int64_t ncols, int lower_tri, void* stream);
+/* Compact grid: G[r][q] = sum_j A[knots[q]][j] * Zm[p(q)][r][j] for every column q of the knot list
+ * (knots[g_ld]: per pulsar the sorted rows of A that its TOAs interpolate, each pulsar block starting at an
+ * even column and padded to even length with -1).  tile_list[n_tiles][4] = {pulsar, first column, columns
+ * (<= 64), k extent} enumerates 64-column blocks, heaviest first; with lower_tri the k loop stops at the
+ * tile's k extent (A[n][j] == 0 for j > n). */
+int ptar_gwb_synth(double* G, int64_t g_ld, const double* A, int64_t lda, const double* Zm, int J, int64_t nreal,
+                   const int32_t* tile_list, int n_tiles, const int32_t* knots, int lower_tri, void* stream);
 
 /* The fused generator: out[r][i] = white + ecorr + red + gwb + det for nreal realizations. */
 int ptar_generate(const ptar_gen_params* p, void* stream);
@@ -162,8 +168,12 @@ typedef struct {
   int64_t lda;
   int32_t Jg;               /* columns of A                                               */
   int32_t lower_tri;
-  double* Zm;               /* scratch [chunk][n_psr][Jg]                                 */
-  double* Gbuf;             /* scratch [chunk][n_psr][npts]                               */
+  const int32_t* tile_list; /* [n_syn_tiles][4], see ptar_gwb_synth                       */
+  const int32_t* knots;     /* [gen.g_ld]                                                 */
+  int32_t n_syn_tiles;
+  int32_t reserved;
+  double* Zm;               /* scratch [n_psr][chunk][Jg]                                 */
+  double* Gbuf;             /* scratch [chunk][gen.g_ld]                                  */
   const double* gwb_zin;    /* parity mode: [nreal][n_psr][Jg] or NULL                    */
 } ptar_job;
 

@@ -38,7 +38,7 @@ class GenParams(C.Structure):
         ("ep_ecorr", C.c_void_p), ("ep_bucket", C.c_void_p), ("ep_gidx", C.c_void_p), ("ep_gw", C.c_void_p),
         ("ep_ginv", C.c_void_p), ("psr_bucket_off", C.c_void_p), ("Ftile", C.c_void_p),
         ("rn_scale", C.c_void_p), ("rn_omega", C.c_void_p),
-        ("G", C.c_void_p),
+        ("G", C.c_void_p), ("g_ld", C.c_int64),
         ("z1", C.c_void_p), ("z2", C.c_void_p), ("zb", C.c_void_p), ("zrn", C.c_void_p),
         ("n_bucket_total", C.c_int64),
         ("seed", C.c_uint64), ("real0", C.c_int64),
@@ -48,7 +48,8 @@ class GenParams(C.Structure):
 
 class Job(C.Structure):
     _fields_ = [("gen", GenParams), ("M", C.c_void_p), ("A", C.c_void_p), ("lda", C.c_int64), ("Jg", C.c_int32),
-                ("lower_tri", C.c_int32), ("Zm", C.c_void_p), ("Gbuf", C.c_void_p), ("gwb_zin", C.c_void_p)]
+                ("lower_tri", C.c_int32), ("tile_list", C.c_void_p), ("knots", C.c_void_p), ("n_syn_tiles", C.c_int32),
+                ("reserved", C.c_int32), ("Zm", C.c_void_p), ("Gbuf", C.c_void_p), ("gwb_zin", C.c_void_p)]
 
 
 _lib = None
@@ -74,7 +75,7 @@ def lib():
     L.ptar_fourier_basis.argtypes = [vp, vp, i64, vp, vp, vp, i32, i32, i64, vp]
     L.ptar_cgw_delay.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i64, vp]
     L.ptar_gwb_mix.argtypes = [vp, vp, vp, i32, i32, i64, u64, i64, vp]
-    L.ptar_gwb_synth.argtypes = [vp, vp, i64, vp, i32, i32, i64, i32, vp]
+    L.ptar_gwb_synth.argtypes = [vp, i64, vp, i64, vp, i32, i64, vp, i32, vp, i32, vp]
     L.ptar_generate.argtypes = [C.POINTER(GenParams), vp]
     L.ptar_philox_normals.argtypes = [vp, i32, i32, i64, i64, i64, u64, vp]
     L.ptar_run_job.argtypes = [C.POINTER(Job), i64, C.c_int32, vp, vp]

@@ -152,55 +152,36 @@ int ptar_gwb_mix(double* Zm, const double* M, const double* zin, int n_psr, int 
   if (!Zm || !M || n_psr <= 0 || J <= 0 || nreal <= 0) return fail(-1, "ptar_gwb_mix: bad argument%s");
   if (!zin && (real0 & 3)) return fail(-2, "ptar_gwb_mix: real0 must be a multiple of 4%s");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const dim3 grid((J + ptar::MIX_JT - 1) / ptar::MIX_JT, static_cast<unsigned>((nreal + 3) / 4));
-  static const bool use_fma = getenv("PTAR_MIX_FMA") != nullptr;  // legacy FMA-pipe kernel, kept for A/B runs
-  if (!use_fma) {
-    const int KP = (n_psr + 3) & ~3, NP = (n_psr + 7) & ~7;
-    const size_t smem = sizeof(double) * (size_t(KP) * ptar::MX_ZS + size_t(NP) * (KP + 4));
-    if (smem > 227 * 1024) return fail(-3, "ptar_gwb_mix: too many pulsars for shared memory%s");
-    if (zin) {
-      cudaFuncSetAttribute(ptar::gwb_mix_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      ptar::gwb_mix_dmma_kernel<true><<<grid, 256, smem, st>>>(Zm, M, zin, n_psr, J, nreal, ptar::philox_keys(seed), real0);
-    } else {
-      cudaFuncSetAttribute(ptar::gwb_mix_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      ptar::gwb_mix_dmma_kernel<false><<<grid, 256, smem, st>>>(Zm, M, zin, n_psr, J, nreal, ptar::philox_keys(seed), real0);
-    }
-    return check_launch("ptar_gwb_mix");
-  }
-  const size_t smem = sizeof(double) * size_t(n_psr) * ptar::MIX_JT * 4;
+  const dim3 grid((J + ptar::MIX_JT - 1) / ptar::MIX_JT,
+                  static_cast<unsigned>((nreal + 4 * ptar::MX_GROUPS - 1) / (4 * ptar::MX_GROUPS)));
+  const int KP = (n_psr + 3) & ~3, NP = (n_psr + 7) & ~7;
+  const size_t smem = sizeof(double) * (size_t(KP) * ptar::MX_ZS + size_t(NP) * (KP + 4));
   if (smem > 227 * 1024) return fail(-3, "ptar_gwb_mix: too many pulsars for shared memory%s");
-  const int nwarps = (n_psr + 3) / 4;
-  const int threads = 32 * (nwarps < 4 ? 4 : (nwarps > 32 ? 32 : nwarps));
   if (zin) {
-    cudaFuncSetAttribute(ptar::gwb_mix_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    ptar::gwb_mix_kernel<true><<<grid, threads, smem, st>>>(Zm, M, zin, n_psr, J, nreal, seed, real0);
+    cudaFuncSetAttribute(ptar::gwb_mix_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    ptar::gwb_mix_dmma_kernel<true><<<grid, 256, smem, st>>>(Zm, M, zin, n_psr, J, nreal, ptar::philox_keys(seed), real0);
   } else {
-    cudaFuncSetAttribute(ptar::gwb_mix_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    ptar::gwb_mix_kernel<false><<<grid, threads, smem, st>>>(Zm, M, zin, n_psr, J, nreal, seed, real0);
+    cudaFuncSetAttribute(ptar::gwb_mix_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    ptar::gwb_mix_dmma_kernel<false><<<grid, 256, smem, st>>>(Zm, M, zin, n_psr, J, nreal, ptar::philox_keys(seed), real0);
   }
   return check_launch("ptar_gwb_mix");
 }
 
-int ptar_gwb_synth(double* G, const double* A, int64_t lda, const double* Zm, int npts, int J, int64_t ncols,
-                   int lower_tri, void* stream) {
-  if (!G || !A || !Zm || npts <= 0 || J <= 0 || ncols <= 0) return fail(-1, "ptar_gwb_synth: bad argument%s");
-  if ((J & 3) || (lda & 1) || lda < J) return fail(-2, "ptar_gwb_synth: need J %% 4 == 0 and even lda >= J%s");
-  static const bool use_fma = getenv("PTAR_SYNTH_FMA") != nullptr;  // legacy FMA-pipe kernel, kept for A/B runs
-  if (use_fma) {
-    const dim3 grid((npts + ptar::SY_BM - 1) / ptar::SY_BM, static_cast<unsigned>((ncols + ptar::SY_BN - 1) / ptar::SY_BN));
-    ptar::gwb_synth_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(G, A, lda, Zm, npts, J, ncols, lower_tri);
-    return check_launch("ptar_gwb_synth");
-  }
-  const int n_tiles = (npts + ptar::DM_BN - 1) / ptar::DM_BN;
-  const int64_t c_tiles = (ncols + ptar::DM_BC - 1) / ptar::DM_BC;
-  if (c_tiles * n_tiles > 0x7fffffffLL) return fail(-3, "ptar_gwb_synth: grid too large%s");
+int ptar_gwb_synth(double* G, int64_t g_ld, const double* A, int64_t lda, const double* Zm, int J, int64_t nreal,
+                   const int32_t* tile_list, int n_tiles, const int32_t* knots, int lower_tri, void* stream) {
+  if (!G || !A || !Zm || !tile_list || !knots || J <= 0 || nreal <= 0 || n_tiles <= 0 || g_ld <= 0)
+    return fail(-1, "ptar_gwb_synth: bad argument%s");
+  if ((J & 3) || (lda & 1) || lda < J || (g_ld & 1)) return fail(-2, "ptar_gwb_synth: need J %% 4 == 0, even lda >= J, even g_ld%s");
+  const int64_t r_blocks = (nreal + ptar::DM_BC - 1) / ptar::DM_BC;
+  if (r_blocks > 65535) return fail(-3, "ptar_gwb_synth: too many realizations per call%s");
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(ptar::gwb_synth_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ptar::DM_SMEM));
     attr_set = true;
   }
-  ptar::gwb_synth_dmma_kernel<<<static_cast<unsigned>(c_tiles * n_tiles), 256, ptar::DM_SMEM, static_cast<cudaStream_t>(stream)>>>(
-      G, A, lda, Zm, npts, J, ncols, lower_tri, static_cast<int>(c_tiles), n_tiles);
+  const dim3 grid(static_cast<unsigned>(n_tiles), static_cast<unsigned>(r_blocks));
+  ptar::gwb_synth_dmma_kernel<<<grid, 256, ptar::DM_SMEM, static_cast<cudaStream_t>(stream)>>>(
+      G, g_ld, A, lda, Zm, J, nreal, tile_list, knots, lower_tri);
   return check_launch("ptar_gwb_synth");
 }
 
@@ -216,8 +197,8 @@ int ptar_generate(const ptar_gen_params* pp, void* stream) {
     return fail(-2, "ptar_generate: white noise needs w1/w2%s");
   if ((p.flags & PTAR_F_ECORR) && (!p.ep_ecorr || !p.ep_bucket)) return fail(-2, "ptar_generate: ECORR needs ep_ecorr/ep_bucket%s");
   if ((p.flags & (PTAR_F_ECORR | PTAR_F_RED)) && (!p.eloc || !p.dtau)) return fail(-2, "ptar_generate: epoch terms need eloc/dtau%s");
-  if ((p.flags & PTAR_F_GWB) && (!p.G || p.npts <= 1 || !p.ep_gidx || !p.ep_gw || !p.ep_ginv || !p.eloc || !p.dtau))
-    return fail(-2, "ptar_generate: GWB needs G, ep_gidx, ep_gw, ep_ginv, eloc, dtau%s");
+  if ((p.flags & PTAR_F_GWB) && (!p.G || p.npts <= 1 || p.g_ld <= 0 || !p.ep_gidx || !p.ep_gw || !p.ep_ginv || !p.eloc || !p.dtau))
+    return fail(-2, "ptar_generate: GWB needs G, g_ld, ep_gidx, ep_gw, ep_ginv, eloc, dtau%s");
   if ((p.flags & PTAR_F_DET) && !p.det) return fail(-2, "ptar_generate: DET needs det%s");
   const bool inject = p.z1 || p.z2 || p.zb || p.zrn;
   if (inject) {
@@ -270,10 +251,12 @@ int ptar_run_job(const ptar_job* job, int64_t real0, int32_t nreal, double* out,
   g.out = out;
   const bool inject = g.z1 || g.z2 || g.zb || g.zrn || job->gwb_zin;
   if (g.flags & PTAR_F_GWB) {
-    if (!job->M || !job->A || !job->Zm || !job->Gbuf) return fail(-2, "ptar_run_job: GWB buffers missing%s");
+    if (!job->M || !job->A || !job->Zm || !job->Gbuf || !job->tile_list || !job->knots)
+      return fail(-2, "ptar_run_job: GWB buffers missing%s");
     int rc = ptar_gwb_mix(job->Zm, job->M, inject ? job->gwb_zin : nullptr, g.n_psr, job->Jg, nreal, g.seed, real0, stream);
     if (rc) return rc;
-    rc = ptar_gwb_synth(job->Gbuf, job->A, job->lda, job->Zm, g.npts, job->Jg, int64_t(nreal) * g.n_psr, job->lower_tri, stream);
+    rc = ptar_gwb_synth(job->Gbuf, g.g_ld, job->A, job->lda, job->Zm, job->Jg, nreal, job->tile_list, job->n_syn_tiles,
+                        job->knots, job->lower_tri, stream);
     if (rc) return rc;
     g.G = job->Gbuf;
   }

@@ -57,9 +57,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 // WHITE 0/1/2 = no white noise / one merged draw / two draws, DET 0/1 = no / with deterministic term
 // (specialised builds of the throughput mode: the flag tests disappear from the inner loop).
 template <int RC, bool INJECT, int WHITE, int DET>
-__global__ void __launch_bounds__(16 * RC, 1024 / (16 * RC)) gen_kernel(const ptar_gen_params P, const PhiloxKeys K) {
+__device__ __forceinline__ void gen_body(const ptar_gen_params& P, const PhiloxKeys& K, const int tile_idx,
+                                         const int chunk_idx, unsigned char* smem_raw) {
   constexpr int GEN_THREADS = 16 * RC;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
   double* Fs = reinterpret_cast<double*>(smem_raw + 16);
   const int J = P.J;
@@ -69,8 +69,8 @@ __global__ void __launch_bounds__(16 * RC, 1024 / (16 * RC)) gen_kernel(const pt
   constexpr int RG = RC / 4;
 
   const int tid = threadIdx.x;
-  const ptar_tile tile = P.tiles[blockIdx.y];   // x = realization chunk (fastest): the CTAs that share a
-  const int r0 = blockIdx.x * RC;               // tile's statics and basis run together and hit L2  // first realization (local to this call)
+  const ptar_tile tile = P.tiles[tile_idx];
+  const int r0 = chunk_idx * RC;  // first realization (local to this call)
   const int nr = min(RC, P.nreal - r0);
   const uint32_t flags = P.flags;
   const bool has_red = (flags & PTAR_F_RED) && J > 0;
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(16 * RC, 1024 / (16 * RC)) gen_kernel(const pt
     __syncthreads();
     if (tid == 0) {
       const uint32_t bytes = static_cast<uint32_t>(sizeof(double) * J * EP);
-      const double* src = P.Ftile + size_t(blockIdx.y) * J * EP;
+      const double* src = P.Ftile + size_t(tile_idx) * J * EP;
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes)
                    : "memory");
       asm volatile(
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(16 * RC, 1024 / (16 * RC)) gen_kernel(const pt
         for (int l = 0; l < 4; ++l) {
           const int r = rg * 4 + l;
           if (r < nr) {
-            const double* Gr = P.G + (size_t(r0 + r) * P.n_psr + psr) * P.npts + j;
+            const double* Gr = P.G + size_t(r0 + r) * P.g_ld + j;
             const double g0 = __ldg(Gr), dg = __ldg(Gr + 1) - g0;
             add0[l] = fma(gwt, dg, g0);
             add1[l] = dg * ginv;
@@ -354,6 +354,14 @@ __global__ void __launch_bounds__(16 * RC, 1024 / (16 * RC)) gen_kernel(const pt
   if (tid < n_pad) {
     for (int r = 0; r < nr; ++r) P.out[size_t(r0 + r) * ld + tile.toa_start + tile.n_toa + tid] = 0.0;
   }
+}
+
+// grid = (realization chunks, tiles); the chunk index is fastest so the CTAs that share a tile's statics and
+// basis run together and hit L2.
+template <int RC, bool INJECT, int WHITE, int DET>
+__global__ void __launch_bounds__(16 * RC, 1024 / (16 * RC)) gen_kernel(const ptar_gen_params P, const PhiloxKeys K) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  gen_body<RC, INJECT, WHITE, DET>(P, K, blockIdx.y, blockIdx.x, smem_raw);
 }
 
 }  // namespace ptar

@@ -151,7 +151,9 @@ def test_planner_epochs_and_tiles():
     ep = ep[:len(mj)]
     for e in np.unique(ep):
         assert len(np.unique(gj[ep == e])) == 1
-        assert pl["ep_gidx"][e] == gj[ep == e][0]
+        assert pl["knots"][pl["ep_gidx"][e]] == gj[ep == e][0]          # compact-grid column -> knot
+        assert pl["knots"][pl["ep_gidx"][e] + 1] == gj[ep == e][0] + 1
+    assert pl["g_ld"] % 2 == 0 and np.all(pl["syn_tiles"][:, 2] <= 64) and np.all(np.diff(pl["syn_tiles"][:, 3]) <= 0)
 
 
 def test_noise_dict_and_synthetic_dataset():
