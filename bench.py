@@ -96,12 +96,11 @@ def run_reference(args):
     ds = recipe.dataset_from_pulsars(psrs, noise)
     cores = min(os.cpu_count() or 1, 64)
     per_step = cores
-    t0 = time.perf_counter()
-    done_total = 0
-    for _ in range(args.steps):
-        _, _, done = cpu_arm(ds, per_step, cores, budget_s=max(20.0, 180.0 / max(args.steps, 1)))
+    done_total, wall = 0, 0.0
+    for _ in range(args.steps):   # a step = one realization per core; pool start-up and one warm-up pass are untimed
+        _, w, done = cpu_arm(ds, per_step, cores, budget_s=max(20.0, 180.0 / max(args.steps, 1)))
         done_total += done
-    wall = time.perf_counter() - t0
+        wall += w
     value = done_total / wall
     ntoa = sum(p.toas.ntoas for p in psrs)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "realizations/s", "n_gpus": args.gpus,
@@ -218,7 +217,10 @@ def main():
     prof = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.isfile(prof):
         with open(prof) as fh:
-            roof["traffic"] = json.load(fh).get("gen_kernel_dram_bytes_per_launch")
+            tj = json.load(fh)
+        roof["traffic"] = tj.get("gen_kernel_dram_bytes_per_launch")
+        roof["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of a 512-realization launch "
+                                "(algorithmic bytes of that launch: %.4g)" % (8.0 * b.n_toa_total * 512))
 
     line = {"metric": METRIC, "value": value, "unit": "realizations/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -62,7 +62,8 @@ def main():
         md.append(f"\nDRAM traffic per launch: {rd + wr:.4g} B (read {rd:.4g} + write {wr:.4g})\n")
         if tkey and tkey in name:
             traffic[f"{tkey}_dram_bytes_per_launch"] = rd + wr
-            traffic[f"{tkey}_duration_us_under_ncu"] = float(d["gpu__time_duration.sum"][0])
+            dur, du = d["gpu__time_duration.sum"]
+            traffic[f"{tkey}_duration_us_under_ncu"] = float(dur) * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(du, 1.0)
             traffic[f"{tkey}_grid"] = d["launch__grid_size"][0]
     src = ncu_csv(rep, "source")
     hi = [i for i, r in enumerate(src) if r and r[0] == "Address"]
