@@ -18,6 +18,19 @@ from .engine import PulsarBatch
 from .simulate import SimulatedPulsar, TimeArray
 
 
+def extrap1d(interpolator):
+    """Flat extrapolation wrapper for a 1-d interpolator exposing ``.x`` / ``.y`` (``red_noise.py:11-33``; used
+    by the reference for ``userSpec``).  ``add_gwb`` / ``PulsarBatch.set_gwb`` apply the same rule vectorised."""
+    xs, ys = np.asarray(interpolator.x), np.asarray(interpolator.y)
+
+    def ufunclike(x):
+        x = np.asarray(x, dtype=float)
+        inside = np.clip(x, xs[0], xs[-1])
+        return np.where(x < xs[0], ys[0], np.where(x > xs[-1], ys[-1], np.asarray(interpolator(inside))))
+
+    return ufunclike
+
+
 def create_fourier_design_matrix_red(toas: np.ndarray, nmodes: int = 30, Tspan: float = None, logf: bool = False,
                                      fmin: float = None, fmax: float = None, pshift: bool = False,
                                      libstempo_convention: bool = False, modes: np.ndarray = None) -> tuple:
