@@ -15,6 +15,7 @@
  *   ptar_gwb_mix           w draws + np.dot(M, w)                       red_noise.py:238-240, :268
  *   ptar_gwb_synth         sqrt(C) scale, Hermitian pack, ifft, crop    red_noise.py:269-285
  *   ptar_cgw_delay         add_cgw arithmetic                           deterministic.py:98-163
+ *   ptar_cw_catalog        loop_over_CWs[_parallel] (numba)             deterministic.py:321-561
  *   ptar_generate          efac/equad draw                              white_noise.py:105-109
  *                          U @ (ecorr*z)                                white_noise.py:182
  *                          F @ (sqrt(prior)*z)                          red_noise.py:126-128
@@ -132,6 +133,15 @@ int ptar_fourier_basis(double* out, const int64_t* row_off, int64_t col_stride,
  * out[i] (+)= delay(t[i]) ; t = mjd*86400 - tref. */
 int ptar_cgw_delay(double* out, const double* t, const int32_t* psr_of_toa, const double* psr_par,
                    const double* src, int mode, int psr_term, int accumulate, int64_t n, void* stream);
+
+/* Sum of many continuous-wave sources for ONE pulsar (add_catalog_of_cws, deterministic.py:188-561; SURVEY.md
+ * 8f row f1).  cat[8][n_src] = gwtheta, gwphi, mc [Msun], dist [Mpc], fgw [Hz], phase0, psi, inc (device);
+ * phat_host[3] = pulsar unit vector (HOST); pdist in kpc or pphase (use_pphase); mode / psr_term as in
+ * ptar_cgw_delay; NaN contributions are dropped like the reference does.  Scratch: pre[n_src][16],
+ * partial[n_slices][n_toa] (device).  out[i] (+)= sum_s delay_s(t[i]); t = mjd*86400 - tref. */
+int ptar_cw_catalog(double* out, const double* t, int64_t n_toa, const double* phat_host, const double* cat,
+                    int64_t n_src, double pdist_kpc, double pphase, int use_pphase, int mode, int psr_term,
+                    int accumulate, double* pre, double* partial, int n_slices, void* stream);
 
 /* Zm[p][r][j] = sum_q M[p][q] z[r][q][j]  (output pulsar-major: [n_psr][nreal][J]).  z is read from
  * zin[r][q][j] (parity) or drawn from Philox (zin == NULL; stream PTAR_K_GWB).  M is n_psr x n_psr lower

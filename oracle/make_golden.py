@@ -228,6 +228,32 @@ def make_flags(ref):
     np.savez(os.path.join(GOLD, "ref_flags.npz"), **store)
 
 
+def make_catalog(ref):
+    """``add_catalog_of_cws`` (deterministic.py:188-318; numba loops :321-561) on the 4 synthetic pulsars with a
+    300-source catalog; source 7 has already merged at the late TOAs (negative frequency -> NaN -> masked)."""
+    spec = synth_flag_pulsars()
+    rng = np.random.default_rng(21)
+    n = 300
+    cat = dict(gwtheta=np.arccos(rng.uniform(-1, 1, n)), gwphi=rng.uniform(0, 2 * np.pi, n),
+               mc=10 ** rng.uniform(8.0, 9.8, n), dist=10 ** rng.uniform(1.0, 3.0, n), fgw=10 ** rng.uniform(-8.8, -7.3, n),
+               phase0=rng.uniform(0, 2 * np.pi, n), psi=rng.uniform(0, np.pi, n), inc=np.arccos(rng.uniform(-1, 1, n)))
+    cat["mc"][7], cat["fgw"][7] = 3e10, 4e-7          # merges inside the data span
+    store = {f"cat_{k}": v for k, v in cat.items()}
+    variants = {"evolve": dict(pdist=1.2, psrTerm=True, evolve=True), "earth": dict(psrTerm=False, evolve=True),
+                "approx": dict(pdist=0.8, psrTerm=True, evolve=False, phase_approx=True),
+                "mono": dict(pdist=0.8, psrTerm=True, evolve=False, phase_approx=False),
+                "pphase": dict(pphase=1.5, psrTerm=True, evolve=True)}
+    for tag, kw in variants.items():
+        for i, s in enumerate(spec):
+            p = refstubs.StubPulsar(s["name"], s["loc"], s["mjd"].astype(np.longdouble), s["err_us"], s["flags"])
+            ref.deterministic.add_catalog_of_cws(p, cat["gwtheta"].copy(), cat["gwphi"].copy(), cat["mc"].copy(), cat["dist"].copy(),
+                                                 cat["fgw"].copy(), cat["phase0"].copy(), cat["psi"].copy(), cat["inc"].copy(),
+                                                 tref=53000 * 86400, **kw)
+            store[f"cat_{tag}_{i}"] = p.signal_seconds(f"{p.name}_cw_catalog")
+    assert any(np.isnan(v).sum() == 0 for v in store.values())
+    np.savez(os.path.join(GOLD, "ref_catalog.npz"), **store)
+
+
 def make_orf(ref):
     rng = np.random.default_rng(3)
     n = 9
@@ -254,6 +280,7 @@ def main():
     make_small(ref)
     make_flags(ref)
     make_orf(ref)
+    make_catalog(ref)
     print("golden fixtures written to", GOLD)
 
 

@@ -268,6 +268,17 @@ def cgw(mjd, loc, gwtheta, gwphi, mc, dist, fgw, phase0, psi, inc, pdist=1.0, pp
     return -fplus * rplus - fcross * rcross
 
 
+def cw_catalog(mjd, loc, cat, **kw):
+    """deterministic.py:443-561 (``loop_over_CWs``): per-source ``cgw`` with NaNs dropped (:553-559), summed."""
+    out = np.zeros(len(mjd))
+    with np.errstate(invalid="ignore"):
+        for k in range(len(cat["mc"])):
+            r = cgw(mjd, loc, cat["gwtheta"][k], cat["gwphi"][k], cat["mc"][k], cat["dist"][k], cat["fgw"][k],
+                    cat["phase0"][k], cat["psi"][k], cat["inc"][k], **kw)
+            out += np.where(np.isnan(r), 0.0, r)
+    return out
+
+
 # --------------------------------------------------------------------------- whole recipes
 def weighted_mean_residual(delay, err):
     """residual formation without PINT."""

@@ -88,6 +88,111 @@ __global__ void cgw_kernel(double* __restrict__ out, const double* __restrict__ 
   out[i] = accumulate ? out[i] + res : res;
 }
 
+// ---------------------------------------------------------------------------------------
+// Catalog of continuous-wave sources (deterministic.py:188-561; the reference's numba loops).
+// cw_prefactor_kernel: the per-source scalars of :340-376 for one pulsar direction ->
+//   pre[s][16] = {w0, fac1, fac2, fac3, phase0/2, w0^-5/3, incfac1, incfac2, cos2psi, sin2psi, fplus, fcross,
+//                 cosMu, pd_sec, -, -}
+// cw_catalog_kernel: thread = one TOA, CTA = 128 TOAs x one slice of the catalog staged through shared memory;
+// NaN contributions (a binary that has already merged, :433-438) are dropped; slices are summed in a fixed order
+// by cw_reduce_kernel so the result is deterministic.
+__global__ void cw_prefactor_kernel(double* __restrict__ pre, const double* __restrict__ cat, int64_t n_src,
+                                    double px, double py, double pz, double pdist_kpc, double pphase, int use_pphase) {
+  const int64_t s = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (s >= n_src) return;
+  const double gwtheta = cat[s], gwphi = cat[n_src + s];
+  const double mc = cat[2 * n_src + s] * 4.925838061995516e-06;     // SOLAR2S (constants.py:6)
+  const double dist = cat[3 * n_src + s] * 102927125054338.98;      // MPC2S   (constants.py:8)
+  const double fgw = cat[4 * n_src + s], phase0 = cat[5 * n_src + s] / 2, psi = cat[6 * n_src + s], inc = cat[7 * n_src + s];
+  const double w0 = 3.141592653589793 * fgw;
+  const double cgt = cos(gwtheta), cgp = cos(gwphi), sgt = sin(gwtheta), sgp = sin(gwphi);
+  const double mx = sgp, my = -cgp;
+  const double nx = -cgt * cgp, ny = -cgt * sgp, nz = sgt;
+  const double ox = -sgt * cgp, oy = -sgt * sgp, oz = -cgt;
+  const double mc53 = pow(mc, 5.0 / 3);
+  const double mdp = mx * px + my * py + 0.0 * pz, ndp = nx * px + ny * py + nz * pz, odp = ox * px + oy * py + oz * pz;
+  const double cosMu = -odp;
+  double pd = use_pphase ? pphase / (2 * 3.141592653589793 * fgw * (1 - cosMu)) / 102927125054.33899 : pdist_kpc;
+  pd *= 102927125054.33899;                                          // KPC2S (constants.py:7)
+  double* o = pre + s * 16;
+  o[0] = w0;
+  o[1] = 256.0 / 5 * mc53 * pow(w0, 8.0 / 3);
+  o[2] = 1.0 / 32 / mc53;
+  o[3] = mc53 / dist;
+  o[4] = phase0;
+  o[5] = pow(w0, -5.0 / 3);
+  o[6] = 0.5 * (3 + cos(2 * inc));
+  o[7] = 2 * cos(inc);
+  o[8] = cos(2 * psi);
+  o[9] = sin(2 * psi);
+  o[10] = 0.5 * (mdp * mdp - ndp * ndp) / (1 + odp);
+  o[11] = (mdp * ndp) / (1 + odp);
+  o[12] = cosMu;
+  o[13] = pd;
+  o[14] = o[15] = 0.0;
+}
+
+constexpr int CW_TOAS = 128, CW_STAGE = 32;
+
+__global__ void __launch_bounds__(CW_TOAS) cw_catalog_kernel(double* __restrict__ partial, const double* __restrict__ t,
+                                                             int64_t n_toa, const double* __restrict__ pre, int64_t n_src,
+                                                             int64_t src_per_slice, int mode, int psr_term) {
+  __shared__ double sp[CW_STAGE][16];
+  const int64_t i = int64_t(blockIdx.x) * CW_TOAS + threadIdx.x;
+  const int64_t s_begin = int64_t(blockIdx.y) * src_per_slice;
+  const int64_t s_end = min(n_src, s_begin + src_per_slice);
+  const double toa = i < n_toa ? t[i] : 0.0;
+  double acc = 0.0;
+  for (int64_t s0 = s_begin; s0 < s_end; s0 += CW_STAGE) {
+    const int64_t rem = s_end - s0;
+    const int cnt = rem < CW_STAGE ? static_cast<int>(rem) : CW_STAGE;
+    __syncthreads();
+    for (int k = threadIdx.x; k < cnt * 16; k += CW_TOAS) sp[k >> 4][k & 15] = pre[(s0 + (k >> 4)) * 16 + (k & 15)];
+    __syncthreads();
+    for (int k = 0; k < cnt; ++k) {
+      const double* q = sp[k];
+      const double w0 = q[0], fac1 = q[1], fac2 = q[2], fac3 = q[3], phase0 = q[4], w053 = q[5];
+      const double tp = toa - q[13] * (1 - q[12]);
+      double omega, omega_p, phase, phase_p;
+      if (mode == 0) {
+        omega = w0 * pow(1 - fac1 * toa, -3.0 / 8);
+        omega_p = w0 * pow(1 - fac1 * tp, -3.0 / 8);
+        phase = phase0 + fac2 * (w053 - pow(omega, -5.0 / 3));
+        phase_p = phase0 + fac2 * (w053 - pow(omega_p, -5.0 / 3));
+      } else if (mode == 1) {
+        omega = w0;
+        omega_p = w0 * pow(1 + fac1 * q[13] * (1 - q[12]), -3.0 / 8);
+        phase = phase0 + omega * toa;
+        phase_p = phase0 + fac2 * (w053 - pow(omega_p, -5.0 / 3)) + omega_p * toa;
+      } else {
+        omega = w0;
+        omega_p = omega;
+        phase = phase0 + omega * toa;
+        phase_p = phase0 + omega * tp;
+      }
+      double s2, c2, s2p, c2p;
+      sincos(2 * phase, &s2, &c2);
+      sincos(2 * phase_p, &s2p, &c2p);
+      const double At = s2 * q[6], Bt = c2 * q[7], Atp = s2p * q[6], Btp = c2p * q[7];
+      const double alpha = fac3 / cbrt(omega), alpha_p = fac3 / cbrt(omega_p);
+      const double rplus = alpha * (At * q[8] + Bt * q[9]), rcross = alpha * (-At * q[9] + Bt * q[8]);
+      const double rplus_p = alpha_p * (Atp * q[8] + Btp * q[9]), rcross_p = alpha_p * (-Atp * q[9] + Btp * q[8]);
+      const double r = psr_term ? q[10] * (rplus_p - rplus) + q[11] * (rcross_p - rcross) : -q[10] * rplus - q[11] * rcross;
+      acc += isnan(r) ? 0.0 : r;
+    }
+  }
+  if (i < n_toa) partial[int64_t(blockIdx.y) * n_toa + i] = acc;
+}
+
+__global__ void cw_reduce_kernel(double* __restrict__ out, const double* __restrict__ partial, int64_t n_toa, int n_slices,
+                                 int accumulate) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_toa) return;
+  double a = 0.0;
+  for (int k = 0; k < n_slices; ++k) a += partial[int64_t(k) * n_toa + i];
+  out[i] = accumulate ? out[i] + a : a;
+}
+
 __global__ void philox_normals_kernel(float* __restrict__ out, int kind, int psr, int64_t realization, int64_t idx0,
                                       int64_t n, uint64_t seed) {
   const int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -145,6 +250,21 @@ int ptar_cgw_delay(double* out, const double* t, const int32_t* psr_of_toa, cons
   cgw_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       out, t, psr_of_toa, psr_par, src, mode, psr_term, accumulate, n);
   return check_launch("ptar_cgw_delay");
+}
+
+int ptar_cw_catalog(double* out, const double* t, int64_t n_toa, const double* phat_host, const double* cat, int64_t n_src,
+                    double pdist_kpc, double pphase, int use_pphase, int mode, int psr_term, int accumulate, double* pre,
+                    double* partial, int n_slices, void* stream) {
+  if (!out || !t || !phat_host || !cat || !pre || !partial || n_toa <= 0 || n_src <= 0 || n_slices <= 0 || mode < 0 || mode > 2)
+    return fail(-1, "ptar_cw_catalog: bad argument%s");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cw_prefactor_kernel<<<static_cast<unsigned>((n_src + 255) / 256), 256, 0, st>>>(pre, cat, n_src, phat_host[0], phat_host[1],
+                                                                                   phat_host[2], pdist_kpc, pphase, use_pphase);
+  const int64_t per = (n_src + n_slices - 1) / n_slices;
+  const dim3 grid(static_cast<unsigned>((n_toa + CW_TOAS - 1) / CW_TOAS), static_cast<unsigned>(n_slices));
+  cw_catalog_kernel<<<grid, CW_TOAS, 0, st>>>(partial, t, n_toa, pre, n_src, per, mode, psr_term);
+  cw_reduce_kernel<<<static_cast<unsigned>((n_toa + 255) / 256), 256, 0, st>>>(out, partial, n_toa, n_slices, accumulate);
+  return check_launch("ptar_cw_catalog");
 }
 
 int ptar_gwb_mix(double* Zm, const double* M, const double* zin, int n_psr, int J, int64_t nreal, uint64_t seed,

@@ -150,3 +150,26 @@ def test_hd_basis_against_reference():
     assert np.max(np.abs(got - z["basis_hd"][0])) < 1e-15
     got = O.hd_basis_l0(z["locs"])
     assert np.max(np.abs(got - z["basis_l6"][0])) < 1e-15
+
+
+CAT_VARIANTS = {"evolve": dict(pdist=1.2, psrTerm=True, evolve=True), "earth": dict(psrTerm=False, evolve=True),
+                "approx": dict(pdist=0.8, psrTerm=True, evolve=False, phase_approx=True),
+                "mono": dict(pdist=0.8, psrTerm=True, evolve=False, phase_approx=False),
+                "pphase": dict(pphase=1.5, psrTerm=True, evolve=True)}
+
+
+def load_catalog():
+    c = np.load(os.path.join(GOLD, "ref_catalog.npz"))
+    return c, {k: c[f"cat_{k}"] for k in ("gwtheta", "gwphi", "mc", "dist", "fgw", "phase0", "psi", "inc")}
+
+
+@pytest.mark.parametrize("tag", sorted(CAT_VARIANTS))
+def test_cw_catalog_oracle_against_reference_numba_loops(tag):
+    """``add_catalog_of_cws`` (numba ``loop_over_CWs``), 300 sources incl. one that merges inside the data span.
+    Evolving branches: numpy vs LLVM ``pow`` differ by an ulp, amplified like in ``add_cgw`` (see test_gpu_parity)."""
+    _, spec = load_flags_case()
+    c, cat = load_catalog()
+    tol = 1e-9 if tag in ("evolve", "earth", "pphase") else TIGHT
+    for i, s in enumerate(spec):
+        got = O.cw_catalog(s["mjd"], s["loc"], cat, tref=53000 * 86400, **CAT_VARIANTS[tag])
+        assert rel_rms(got, c[f"cat_{tag}_{i}"]) < tol
