@@ -170,8 +170,10 @@ def main():
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
-        sampler.start()          # samples span warm-up + timed region (both are the same load)
-        time.sleep(0.3)
+        sampler.start()          # samples span warm-up, the timed region and a short soak of the same steps
+        t_wait = time.time()
+        while not sampler.samples and time.time() - t_wait < 8.0:
+            time.sleep(0.05)     # nvidia-smi can take a second to deliver its first sample
     for k in range(args.warmup):
         step(k)
     torch.cuda.synchronize()
@@ -192,7 +194,18 @@ def main():
     for k in range(args.steps):
         step(args.warmup + args.steps + k, timers)
     torch.cuda.synchronize()
-    clocks = sampler.finish() if sampler else None
+    if sampler:
+        # the timed region lasts ~10-20 ms, shorter than nvidia-smi's 100 ms period: keep the identical load
+        # running for ~0.7 s so that the clock / throttle record is taken under this load
+        n0, t_soak, k = len(sampler.samples), time.time(), 0
+        while time.time() - t_soak < 0.7:
+            step(args.warmup + 2 * args.steps + k)
+            torch.cuda.synchronize()
+            k += 1
+        clocks = sampler.finish()
+        clocks["window"] = "warm-up + timed region + %d soak steps of the same load (%d samples before the soak)" % (k, n0)
+    else:
+        clocks = None
     tms = torch.tensor([ms], dtype=torch.float64, device=b.device)
     if dist is not None:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
