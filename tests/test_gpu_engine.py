@@ -166,6 +166,29 @@ def test_shards_and_chunks_are_bitwise_reproducible():
     assert torch.equal(full.cpu(), h)
 
 
+def test_ragged_realization_counts():
+    """nreal not a multiple of the Philox group (4), the CTA chunk (16) or the GWB chunk: a prefix of a
+    longer run, bit for bit; single-pulsar / single-signal batches; a chunk that is not a multiple of 16."""
+    import torch
+    from pta_replicator_b200.engine import PulsarBatch
+    _, spec = load_flags_case()
+    psrs = _psrs(spec)
+    b = _batch(psrs, spec)
+    full = b.generate(64, seed=21, real0=4)
+    for n in (1, 3, 5, 17, 37, 63):
+        assert torch.equal(b.generate(n, seed=21, real0=4), full[:n]), n
+    b.default_chunk = 20                      # chunks of 20 realizations: 16 + 4 per CTA column
+    assert torch.equal(b.generate(64, seed=21, real0=4), full)
+    host = b.generate_to_host(37, seed=21, real0=4, chunk=12)
+    assert torch.equal(host, full[:37].cpu())
+    one = PulsarBatch(psrs[:1])
+    one.set_gwb(-14.0, 4.0)
+    x = one.generate(7, seed=1)
+    assert torch.isfinite(x).all() and x.shape == (7, one.ld) and float(x.abs().max()) > 0
+    with pytest.raises(Exception, match="multiple of 4"):
+        b.generate(8, seed=21, real0=2)
+
+
 def test_distribution_white_ecorr_and_merged_draw():
     """Per-TOA variance of white + ECORR over 4096 realizations; the single-draw variant (PTAR_F_WHITE1)
     has the same variance; an ECORR-only run is constant inside an epoch with variance ecorr^2."""
