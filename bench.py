@@ -129,6 +129,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--split", action="store_true", help="epoch kernel + TOA kernel (two launches) instead of the fused generator")
     ap.add_argument("--gather", action="store_true", help="also time an NCCL all-gather of one chunk of residuals")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -157,6 +158,7 @@ def main():
     synthetic.ng15_recipe(b, noise)
     if args.chunk:
         b.default_chunk = args.chunk
+    b.split_epoch = bool(args.split)
     st = b.compile()
     R = args.nreal
     out = torch.empty((R, b.ld), dtype=torch.float64, device=b.device)
@@ -251,6 +253,7 @@ def main():
     if world == 1 and not args.merged_white and not args.no_variants:
         b1 = PulsarBatch(psrs)
         b1.white_merged = True
+        b1.split_epoch = bool(args.split)
         synthetic.ng15_recipe(b1, noise)
         if args.chunk:
             b1.default_chunk = args.chunk

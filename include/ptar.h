@@ -65,7 +65,7 @@ typedef struct {
   int32_t n_ep;        /* kernel-epochs touched (<= PTAR_TILE_EPOCHS)                   */
   int32_t psr;         /* pulsar index                                                  */
   int32_t nd;          /* Taylor terms used for red noise inside epochs (1..3)          */
-  int32_t reserved;
+  int32_t reserved;    /* c_row0: sum of n_ep over the preceding tiles (rows of the Cbuf blocks)        */
 } ptar_tile;
 
 typedef struct {
@@ -112,6 +112,10 @@ typedef struct {
   int64_t ld_out;
   int32_t nreal;
   int32_t rc;         /* realizations per CTA: 16 (256 threads) or 32 (512 threads); 0 = default */
+  /* optional scratch for the two-kernel schedule (epoch kernel -> TOA kernel): at least
+   * (sum of n_ep over tiles) * ceil(nreal/16) * 50 doubles; NULL selects the fused kernel */
+  double* Cbuf;
+  int64_t cbuf_len;   /* doubles available at Cbuf */
 } ptar_gen_params;
 
 int         ptar_version(void);
@@ -159,6 +163,11 @@ int ptar_gwb_synth(double* G, int64_t g_ld, const double* A, int64_t lda, const 
 
 /* The fused generator: out[r][i] = white + ecorr + red + gwb + det for nreal realizations. */
 int ptar_generate(const ptar_gen_params* p, void* stream);
+
+/* The two launches of the two-kernel schedule one at a time (p->Cbuf != NULL): stage 1 = epoch kernel
+ * (Fourier GEMM, ECORR, GWB grid -> Cbuf), stage 2 = TOA kernel (Cbuf + white noise -> out).  ptar_generate
+ * issues both; this entry exists so a caller can time them separately. */
+int ptar_generate_stage(const ptar_gen_params* p, int stage, void* stream);
 
 /* Raw throughput-mode normals (fp32 Box-Muller of Philox4x32-10), for tests:
  * out[k] = normal(kind, psr, realization, idx0 + k), k < n.  Counter = (idx, kind | psr << 8,

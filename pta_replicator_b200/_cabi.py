@@ -20,7 +20,7 @@ F_WHITE, F_ECORR, F_RED, F_GWB, F_DET, F_WHITE1 = 1, 2, 4, 8, 16, 32
 K_WHITE1, K_WHITE2, K_ECORR, K_RED, K_GWB = 1, 2, 3, 4, 5
 
 EXPORTS = ("ptar_version", "ptar_last_error", "ptar_cholesky_lower", "ptar_fourier_basis", "ptar_cgw_delay", "ptar_cw_catalog",
-           "ptar_gwb_mix", "ptar_gwb_synth", "ptar_generate", "ptar_philox_normals", "ptar_run_job",
+           "ptar_gwb_mix", "ptar_gwb_synth", "ptar_generate", "ptar_generate_stage", "ptar_philox_normals", "ptar_run_job",
            "ptar_run_job_to_host")
 
 
@@ -43,6 +43,7 @@ class GenParams(C.Structure):
         ("n_bucket_total", C.c_int64),
         ("seed", C.c_uint64), ("real0", C.c_int64),
         ("out", C.c_void_p), ("ld_out", C.c_int64), ("nreal", C.c_int32), ("rc", C.c_int32),
+        ("Cbuf", C.c_void_p), ("cbuf_len", C.c_int64),
     ]
 
 
@@ -78,6 +79,7 @@ def lib():
     L.ptar_gwb_mix.argtypes = [vp, vp, vp, i32, i32, i64, u64, i64, vp]
     L.ptar_gwb_synth.argtypes = [vp, i64, vp, i64, vp, i32, i64, vp, i32, vp, i32, vp]
     L.ptar_generate.argtypes = [C.POINTER(GenParams), vp]
+    L.ptar_generate_stage.argtypes = [C.POINTER(GenParams), i32, vp]
     L.ptar_philox_normals.argtypes = [vp, i32, i32, i64, i64, i64, u64, vp]
     L.ptar_run_job.argtypes = [C.POINTER(Job), i64, C.c_int32, vp, vp]
     L.ptar_run_job_to_host.argtypes = [C.POINTER(Job), i64, i64, C.c_int32, vp, vp, vp, vp, vp]

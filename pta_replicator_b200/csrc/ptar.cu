@@ -202,19 +202,37 @@ __global__ void philox_normals_kernel(float* __restrict__ out, int kind, int psr
   out[k] = z[realization & 3];
 }
 
-template <int RC, bool INJECT, int WHITE, int DET>
-int launch_gen(const ptar_gen_params& p, cudaStream_t st) {
-  const size_t smem = ptar::gen_smem_bytes(p.J, RC);
+template <int RC, bool INJECT, int WHITE, int DET, int STAGE>
+int launch_stage(const ptar_gen_params& p, cudaStream_t st) {
+  // STAGE 2 only needs the Cs block; STAGE 0/1 need the GEMM operands
+  size_t smem = ptar::gen_smem_bytes(p.J, RC);
+  if (STAGE == 2) smem = 16 + sizeof(double) * ptar::EP * ptar::gen_css(RC);
   if (smem > 227 * 1024) return fail(-3, "ptar_generate: J too large for shared memory%s");
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
-    cudaFuncSetAttribute(ptar::gen_kernel<RC, INJECT, WHITE, DET>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(ptar::gen_kernel<RC, INJECT, WHITE, DET, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
   const dim3 grid((p.nreal + RC - 1) / RC, p.n_tiles);
   if (grid.y > 65535) return fail(-3, "ptar_generate: more than 65535 tiles%s");
-  ptar::gen_kernel<RC, INJECT, WHITE, DET><<<grid, ptar::gen_threads(RC), smem, st>>>(p, ptar::philox_keys(p.seed));
+  ptar::gen_kernel<RC, INJECT, WHITE, DET, STAGE><<<grid, ptar::gen_threads(RC), smem, st>>>(p, ptar::philox_keys(p.seed));
   return check_launch("ptar_generate");
+}
+
+thread_local int g_only_stage = 0;  // set by ptar_generate_stage: 1 = epoch kernel only, 2 = TOA kernel only
+
+template <int RC, bool INJECT, int WHITE, int DET>
+int launch_gen(const ptar_gen_params& p, cudaStream_t st) {
+  const bool has_epoch = (p.flags & (PTAR_F_RED | PTAR_F_ECORR | PTAR_F_GWB)) != 0;
+  if (p.Cbuf && has_epoch) {  // two-kernel schedule
+    if (g_only_stage != 2) {
+      const int rc = launch_stage<RC, INJECT, -1, -1, 1>(p, st);   // the epoch kernel does not depend on WHITE / DET
+      if (rc || g_only_stage == 1) return rc;
+    }
+    return launch_stage<RC, INJECT, WHITE, DET, 2>(p, st);
+  }
+  if (g_only_stage == 1) return 0;   // nothing to do: no epoch terms (or fused schedule)
+  return launch_stage<RC, INJECT, WHITE, DET, 0>(p, st);
 }
 
 }  // namespace
@@ -328,6 +346,10 @@ int ptar_generate(const ptar_gen_params* pp, void* stream) {
   } else if (p.real0 & 3) {
     return fail(-2, "ptar_generate: real0 must be a multiple of 4%s");
   }
+  if (p.Cbuf) {
+    const ptar_tile* dummy = nullptr; (void)dummy;
+    if (p.cbuf_len <= 0) return fail(-2, "ptar_generate: Cbuf given without cbuf_len%s");
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int rc = p.rc ? p.rc : 16;
   if (rc != 16 && rc != 32) return fail(-2, "ptar_generate: rc must be 16 or 32%s");
@@ -352,6 +374,15 @@ int ptar_generate(const ptar_gen_params* pp, void* stream) {
     case 4: return launch_gen<16, false, 2, 0>(p, st);
     default: return launch_gen<16, false, 2, 1>(p, st);
   }
+}
+
+int ptar_generate_stage(const ptar_gen_params* pp, int stage, void* stream) {
+  if (stage < 1 || stage > 2) return fail(-1, "ptar_generate_stage: stage must be 1 (epoch kernel) or 2 (TOA kernel)%s");
+  if (!pp || !pp->Cbuf) return fail(-2, "ptar_generate_stage: needs the two-kernel schedule (Cbuf)%s");
+  g_only_stage = stage;
+  const int rc = ptar_generate(pp, stream);
+  g_only_stage = 0;
+  return rc;
 }
 
 int ptar_philox_normals(float* out, int kind, int psr, int64_t realization, int64_t idx0, int64_t n, uint64_t seed,

@@ -56,7 +56,11 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 // WHITE / DET: -1 = decided at run time from P.flags (generic build, used by the parity mode);
 // WHITE 0/1/2 = no white noise / one merged draw / two draws, DET 0/1 = no / with deterministic term
 // (specialised builds of the throughput mode: the flag tests disappear from the inner loop).
-template <int RC, bool INJECT, int WHITE, int DET>
+// STAGE 0: fused (epoch stage + TOA stage in one CTA); STAGE 1: epoch stage only, the per-(tile, chunk) block
+// Cs[n_ep][CSS] goes to P.Cbuf; STAGE 2: TOA stage only, the block comes back with one bulk-async copy.
+// Splitting costs ~20 % extra HBM traffic but the TOA-stage warps no longer share their SM with warps that
+// sit in the epoch stage's barriers and load latencies.
+template <int RC, bool INJECT, int WHITE, int DET, int STAGE>
 __device__ __forceinline__ void gen_body(const ptar_gen_params& P, const PhiloxKeys& K, const int tile_idx,
                                          const int chunk_idx, unsigned char* smem_raw) {
   constexpr int GEN_THREADS = 16 * RC;
@@ -81,6 +85,39 @@ __device__ __forceinline__ void gen_body(const ptar_gen_params& P, const PhiloxK
   const uint32_t psr = static_cast<uint32_t>(tile.psr);
   const uint64_t rgroup0 = static_cast<uint64_t>(P.real0 + r0) >> 2;
 
+  const int n_chunks = (P.nreal + RC - 1) / RC;
+  double* cblock = (STAGE != 0 && P.Cbuf)
+                       ? P.Cbuf + (size_t(tile.reserved) * n_chunks + size_t(chunk_idx) * tile.n_ep) * CSS
+                       : nullptr;
+  if (STAGE == 2) {
+    if (has_epoch) {  // fetch the block the epoch kernel left for this (tile, chunk)
+      if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      }
+      __syncthreads();
+      if (tid == 0) {
+        const uint32_t bytes = static_cast<uint32_t>(sizeof(double) * tile.n_ep * CSS);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes)
+                     : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                smem_u32(Cs)),
+            "l"(cblock), "r"(bytes), "r"(smem_u32(mbar))
+            : "memory");
+      }
+      uint32_t done = 0;
+      while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(mbar))
+            : "memory");
+      }
+    }
+  } else {
   // ---- epoch stage -------------------------------------------------------------------
   // GEMM ownership: thread -> realization rr, epochs e0..e0+3, slice ks of the J columns.  Tiles with
   // few epochs split the column range 2- or 4-way so that all 8 warps work (split-K, reduced through
@@ -267,6 +304,14 @@ __device__ __forceinline__ void gen_body(const ptar_gen_params& P, const PhiloxK
   }
   if (has_epoch) __syncthreads();
 
+    if (STAGE == 1) {
+      if (has_epoch) {
+        const int n = tile.n_ep * CSS;
+        for (int idx = tid; idx < n; idx += GEN_THREADS) __stcg(cblock + idx, Cs[idx]);
+      }
+      return;
+    }
+  }
   // ---- TOA stage ---------------------------------------------------------------------
   const bool has_white = WHITE >= 0 ? (WHITE > 0) : ((flags & PTAR_F_WHITE) != 0);
   const bool two_draws = WHITE >= 0 ? (WHITE == 2) : (has_white && !(flags & PTAR_F_WHITE1));
@@ -358,10 +403,10 @@ __device__ __forceinline__ void gen_body(const ptar_gen_params& P, const PhiloxK
 
 // grid = (realization chunks, tiles); the chunk index is fastest so the CTAs that share a tile's statics and
 // basis run together and hit L2.
-template <int RC, bool INJECT, int WHITE, int DET>
+template <int RC, bool INJECT, int WHITE, int DET, int STAGE>
 __global__ void __launch_bounds__(16 * RC, 1024 / (16 * RC)) gen_kernel(const ptar_gen_params P, const PhiloxKeys K) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  gen_body<RC, INJECT, WHITE, DET>(P, K, blockIdx.y, blockIdx.x, smem_raw);
+  gen_body<RC, INJECT, WHITE, DET, STAGE>(P, K, blockIdx.y, blockIdx.x, smem_raw);
 }
 
 }  // namespace ptar

@@ -160,6 +160,12 @@ def test_shards_and_chunks_are_bitwise_reproducible():
     assert torch.equal(full, d)
     e = b.generate(40, seed=4, real0=8)
     assert not torch.equal(full, e)
+    b.split_epoch = True                      # epoch kernel + TOA kernel: same arithmetic, same bits
+    b.default_chunk = 512
+    b._job_cache_key = None
+    assert torch.equal(b.generate(40, seed=3, real0=8), full)
+    b.split_epoch = False
+    b._job_cache_key = None
     wide = b.generate(40, seed=3, real0=8, rc=32)          # 512-thread CTAs, 32 realizations each
     assert torch.equal(full, wide)
     h = b.generate_to_host(40, seed=3, real0=8, chunk=16)
