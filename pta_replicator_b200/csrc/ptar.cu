@@ -346,10 +346,7 @@ int ptar_generate(const ptar_gen_params* pp, void* stream) {
   } else if (p.real0 & 3) {
     return fail(-2, "ptar_generate: real0 must be a multiple of 4%s");
   }
-  if (p.Cbuf) {
-    const ptar_tile* dummy = nullptr; (void)dummy;
-    if (p.cbuf_len <= 0) return fail(-2, "ptar_generate: Cbuf given without cbuf_len%s");
-  }
+  if (p.Cbuf && p.cbuf_len <= 0) return fail(-2, "ptar_generate: Cbuf given without cbuf_len%s");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int rc = p.rc ? p.rc : 16;
   if (rc != 16 && rc != 32) return fail(-2, "ptar_generate: rc must be 16 or 32%s");

@@ -13,8 +13,9 @@
 //   * the Fourier projection F_e . a_r -- a [64 x J] x [J x 3RC] fp64 GEMM on the FMA pipe whose
 //     three right-hand sides are the coefficient vector and its first two time derivatives, so
 //     TOAs inside an epoch (sub-band TOAs < 1 s apart) are reached by a 2nd-order Taylor step whose
-//     remainder is below fp64 rounding of the direct sum (the host picks nd per tile from
-//     |omega_max dt|; single-TOA epochs are exact, nd = 1);
+//     remainder is below fp64 rounding of the direct sum (the host picks the window and nd per tile
+//     from the amplitude-weighted moments of omega, engine._taylor_moments; single-TOA epochs are
+//     exact, nd = 1);
 //   * the GWB grid interpolation (epochs never straddle a grid knot, so it is exactly linear in dt);
 //   * the ECORR draw of the epoch's bucket.
 // The basis tile F [J][64] arrives by one bulk-async (TMA) copy that overlaps the Philox generation
@@ -22,6 +23,7 @@
 // four consecutive realizations (= the four outputs of one Philox counter), so per 4 outputs it
 // spends two Philox calls, four Box-Muller pairs, six 128-bit shared loads, a Horner step and four
 // coalesced 8-byte stores -- the only HBM traffic that scales with R x N_toa.
+// The two stages can also run as two kernels (STAGE template parameter, ptar_generate_stage).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
