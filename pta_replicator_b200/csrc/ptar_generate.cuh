@@ -344,11 +344,16 @@ __device__ __forceinline__ void gen_body(const ptar_gen_params& P, const PhiloxK
         const double2* c2 = reinterpret_cast<const double2*>(Cs + el * CSS + rg * 12);
         const double2 q0 = c2[0], q1 = c2[1], q2 = c2[2], q3 = c2[3], q4 = c2[4], q5 = c2[5];
         // (c0,c1,c2) x 4 realizations = q0.x q0.y q1.x | q1.y q2.x q2.y | q3.x q3.y q4.x | q4.y q5.x q5.y
-        if (nd > 1) {
+        if (nd > 2) {
           v[0] = fma(dt, fma(dt, q1.x, q0.y), q0.x);
           v[1] = fma(dt, fma(dt, q2.y, q2.x), q1.y);
           v[2] = fma(dt, fma(dt, q4.x, q3.y), q3.x);
           v[3] = fma(dt, fma(dt, q5.y, q5.x), q4.y);
+        } else if (nd > 1) {  // (c0, c1) only
+          v[0] = fma(dt, q0.y, q0.x);
+          v[1] = fma(dt, q2.x, q1.y);
+          v[2] = fma(dt, q3.y, q3.x);
+          v[3] = fma(dt, q5.x, q4.y);
         } else {
           v[0] = q0.x; v[1] = q1.y; v[2] = q3.x; v[3] = q4.y;
         }
