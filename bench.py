@@ -141,14 +141,15 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if rank == 0:
-        ge.build()
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        dist.barrier()
+    if rank == 0:
+        ge.build()               # no-op when the in-tree .so is up to date
+    if dist is not None:
+        dist.barrier()           # the other ranks load the library only after rank 0 has (re)built it
     from pta_replicator_b200 import _cabi, synthetic
     from pta_replicator_b200.engine import PulsarBatch
 

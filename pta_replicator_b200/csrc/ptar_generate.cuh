@@ -28,6 +28,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "../../include/ptar.h"
 #include "ptar_rng.cuh"
 
@@ -215,19 +217,23 @@ __device__ __forceinline__ void gen_body(const ptar_gen_params& P, const PhiloxK
     // C[e][r][d] = sum_j F[j][e] * A[d][j][r]   (this thread: columns [jlo, jhi))
     if (e0 < tile.n_ep) {
       const int jlo = (J * ks) / nsplit, jhi = (J * (ks + 1)) / nsplit;
-      for (int j = jlo; j < jhi; ++j) {
-        const double2 f01 = *reinterpret_cast<const double2*>(Fs + j * EP + e0);
-        const double2 f23 = *reinterpret_cast<const double2*>(Fs + j * EP + e0 + 2);
-        const double f[4] = {f01.x, f01.y, f23.x, f23.y};
+      auto gemm = [&](auto ND) {  // one instantiation per Taylor order: no predicated-off FMAs in the loop
+        constexpr int kNd = decltype(ND)::value;
+        for (int j = jlo; j < jhi; ++j) {
+          const double2 f01 = *reinterpret_cast<const double2*>(Fs + j * EP + e0);
+          const double2 f23 = *reinterpret_cast<const double2*>(Fs + j * EP + e0 + 2);
+          const double f[4] = {f01.x, f01.y, f23.x, f23.y};
 #pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          if (d < nd) {
+          for (int d = 0; d < kNd; ++d) {
             const double a = As[(d * J + j) * RC + rr];
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc[i][d] = fma(f[i], a, acc[i][d]);
           }
         }
-      }
+      };
+      if (nd >= 3) gemm(std::integral_constant<int, 3>{});
+      else if (nd == 2) gemm(std::integral_constant<int, 2>{});
+      else gemm(std::integral_constant<int, 1>{});
     }
     __syncthreads();  // everyone is done reading Fs / As: Cs may overwrite them
     if (nsplit > 1) {  // split-K reduction: groups ks >= 1 park their partial sums in rows ks*eper + e
