@@ -234,9 +234,12 @@ def main():
     if os.path.isfile(prof):
         with open(prof) as fh:
             tj = json.load(fh)
-        roof["traffic"] = tj.get("gen_kernel_dram_bytes_per_launch")
-        roof["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of a 512-realization launch "
-                                "(algorithmic bytes of that launch: %.4g)" % (8.0 * b.n_toa_total * 512))
+        cap_real = float(tj.get("gen_kernel_realizations_per_launch", 512))
+        cap_bytes = float(tj.get("gen_kernel_dram_bytes_per_launch", 0.0))
+        roof["traffic"] = cap_bytes / cap_real * (R * args.steps / n_gen)
+        roof["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of a %d-realization "
+                                "launch (%.4g B; algorithmic %.4g B)%s" % (cap_real, cap_bytes, 8.0 * b.n_toa_total * cap_real,
+                                "" if cap_real == R * args.steps / n_gen else ", scaled to this run's realizations per launch"))
 
     line = {"metric": METRIC, "value": value, "unit": "realizations/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -38,6 +38,7 @@ def to_bytes(v, unit):
 def main():
     rep, stem = sys.argv[1], sys.argv[2]
     tkey = sys.argv[sys.argv.index("--traffic-key") + 1] if "--traffic-key" in sys.argv else None
+    rpl = int(sys.argv[sys.argv.index("--real-per-launch") + 1]) if "--real-per-launch" in sys.argv else None
     raw = ncu_csv(rep, "raw")
     hdr, units = raw[0], raw[1]
     md = [f"# ncu summary of `{rep.split('/')[-1]}`  (--set full --clock-control none)\n"]
@@ -65,6 +66,8 @@ def main():
             dur, du = d["gpu__time_duration.sum"]
             traffic[f"{tkey}_duration_us_under_ncu"] = float(dur) * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(du, 1.0)
             traffic[f"{tkey}_grid"] = d["launch__grid_size"][0]
+            if rpl:
+                traffic[f"{tkey}_realizations_per_launch"] = rpl
     src = ncu_csv(rep, "source")
     hi = [i for i, r in enumerate(src) if r and r[0] == "Address"]
     if hi:
