@@ -40,7 +40,7 @@ namespace ptar {
 __host__ __device__ constexpr int gen_threads(int RC) { return 16 * RC; }
 constexpr int EP = PTAR_TILE_EPOCHS;  // 64
 #ifndef GEN_UNROLL
-#define GEN_UNROLL 1
+#define GEN_UNROLL 2  // two realization groups in flight per thread: +1.4 % measured (4: same)
 #endif
 constexpr int kGenUnroll = GEN_UNROLL;
 
