@@ -306,7 +306,7 @@ def main():
                    "d2h_bytes_per_step": int(Re * b.ld * 8), "realizations_per_step_per_gpu": Re, "steps": ne2e,
                    "path": "ptar_run_job_to_host: pinned H2D of noise parameters, generate in chunks of 32, D2H of every residual overlapped on a second stream"}
 
-    if args.gather and dist is not None:
+    if dist is not None:   # final NCCL all-gather of residuals (north star): timed separately on a bounded block
         n = min(R, 64)
         full = torch.empty((world * n, b.ld), dtype=torch.float64, device=b.device)
         dist.all_gather_into_tensor(full, out[:n])
@@ -317,8 +317,11 @@ def main():
         g1.record()
         torch.cuda.synchronize()
         gms = g0.elapsed_time(g1)
+        gather_rate = world * n / (gms * 1e-3)           # realizations/s the gather alone can deliver to every rank
         line["allgather"] = {"realizations_per_rank": n, "ms": gms, "recv_GBps_per_gpu": (world - 1) * n * b.ld * 8 / gms / 1e6,
-                             "note": "final NCCL all-gather of residuals; not in `value` (NVLink-bound, ~8x slower per byte than generation)"}
+                             "value_if_every_realization_were_gathered": 1.0 / (1.0 / value + 1.0 / gather_rate),
+                             "note": "final NCCL all_gather_into_tensor of residuals, not in `value`: NVLink moves 8 B/TOA/realization "
+                                     "~6x slower than one GPU generates them; the last key is the serial (un-overlapped) estimate"}
 
     # ---- CPU baseline (rank 0, N == 1 only): oracle port on the host cores, bounded sample
     if rank == 0 and world == 1 and not args.no_cpu:
