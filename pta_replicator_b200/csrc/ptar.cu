@@ -219,6 +219,22 @@ int launch_stage(const ptar_gen_params& p, cudaStream_t st) {
   return check_launch("ptar_generate");
 }
 
+// Epoch kernel of the two-kernel schedule (RC = 16 blocks of Cbuf, two per CTA).
+template <bool INJECT>
+int launch_epoch(const ptar_gen_params& p, cudaStream_t st) {
+  const size_t smem = ptar::epoch_smem_bytes(p.J);
+  if (smem > 227 * 1024) return fail(-3, "ptar_generate: J too large for shared memory%s");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(ptar::epoch_kernel<INJECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  const dim3 grid((p.nreal + ptar::EPK_RB - 1) / ptar::EPK_RB, p.n_tiles);
+  if (grid.y > 65535) return fail(-3, "ptar_generate: more than 65535 tiles%s");
+  ptar::epoch_kernel<INJECT><<<grid, ptar::EPK_THREADS, smem, st>>>(p, ptar::philox_keys(p.seed));
+  return check_launch("ptar_generate (epoch kernel)");
+}
+
 thread_local int g_only_stage = 0;  // set by ptar_generate_stage: 1 = epoch kernel only, 2 = TOA kernel only
 
 template <int RC, bool INJECT, int WHITE, int DET>
@@ -226,7 +242,8 @@ int launch_gen(const ptar_gen_params& p, cudaStream_t st) {
   const bool has_epoch = (p.flags & (PTAR_F_RED | PTAR_F_ECORR | PTAR_F_GWB)) != 0;
   if (p.Cbuf && has_epoch) {  // two-kernel schedule
     if (g_only_stage != 2) {
-      const int rc = launch_stage<RC, INJECT, -1, -1, 1>(p, st);   // the epoch kernel does not depend on WHITE / DET
+      // the epoch kernel does not depend on WHITE / DET
+      const int rc = RC == 16 ? launch_epoch<INJECT>(p, st) : launch_stage<RC, INJECT, -1, -1, 1>(p, st);
       if (rc || g_only_stage == 1) return rc;
     }
     return launch_stage<RC, INJECT, WHITE, DET, 2>(p, st);

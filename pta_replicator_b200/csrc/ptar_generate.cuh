@@ -422,4 +422,284 @@ __global__ void __launch_bounds__(16 * RC, 1024 / (16 * RC)) gen_kernel(const pt
   gen_body<RC, INJECT, WHITE, DET, STAGE>(P, K, blockIdx.y, blockIdx.x, smem_raw);
 }
 
+// ---- standalone epoch kernel (two-kernel schedule) ------------------------------------------------------
+// Same arithmetic as the epoch stage of gen_body (same summation order, so the two schedules agree bit for bit),
+// blocked for the FP64 pipe instead of for co-residency with the TOA stage: one CTA = one tile x 32
+// realizations (two 16-realization blocks of P.Cbuf); a thread accumulates 4 epochs x 2 realizations x 3 Taylor
+// orders (24 DFMA per five 128-bit shared loads) and writes its 6 coefficients per epoch straight to Cbuf.
+// The ECORR draw and the GWB grid interpolation (scattered reads of G, the long-latency part) are fetched
+// first, into their own shared array, so their latency hides behind the coefficient generation and the GEMM.
+// 16 + 8 (160 J + 4096) bytes of shared memory: 109.6 KB at J = 60 -> 2 CTAs per SM.
+constexpr int EPK_RB = 32;
+constexpr int EPK_THREADS = 256;
+constexpr int EPK_CSS = gen_css(16);  // row pitch of a Cbuf block (must match the TOA kernel's RC = 16 build)
+
+__host__ __device__ inline size_t epoch_smem_bytes(int J) {
+  size_t ops = size_t(J) * EP + size_t(3) * J * EPK_RB;  // Fs[J][64] + As[3][J][32]
+  const size_t scratch = size_t(3) * 24 * 64;             // split-K partial sums alias the operands
+  if (ops < scratch) ops = scratch;
+  return 16 + sizeof(double) * (ops + size_t(EP) * EPK_RB * 2);  // + Add[64][32][2]
+}
+
+template <bool INJECT>
+__global__ void __launch_bounds__(EPK_THREADS, 2) epoch_kernel(const ptar_gen_params P, const PhiloxKeys K) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
+  double* Fs = reinterpret_cast<double*>(smem_raw + 16);
+  const int J = P.J;
+  constexpr int RB = EPK_RB, CSS = EPK_CSS, RG = RB / 4;
+  double* As = Fs + size_t(J) * EP;
+  const size_t ops = size_t(J) * EP + size_t(3) * J * RB;
+  double* Add = Fs + (ops < size_t(3) * 24 * 64 ? size_t(3) * 24 * 64 : ops);  // [epoch][realization][c0 add, c1 add]
+
+  const int tid = threadIdx.x;
+  const int tile_idx = blockIdx.y;
+  const ptar_tile tile = P.tiles[tile_idx];
+  const int r0 = blockIdx.x * RB;
+  const int nr = min(RB, P.nreal - r0);
+  const uint32_t flags = P.flags;
+  const bool has_red = (flags & PTAR_F_RED) && J > 0;
+  const bool has_ecorr = (flags & PTAR_F_ECORR) != 0;
+  const bool has_gwb = (flags & PTAR_F_GWB) && P.npts > 0;
+  const bool has_add = has_ecorr || has_gwb;
+  const int nd = tile.nd;
+  const uint32_t psr = static_cast<uint32_t>(tile.psr);
+  const uint64_t rgroup0 = static_cast<uint64_t>(P.real0 + r0) >> 2;
+  const int n_chunks = (P.nreal + 15) / 16;
+
+  if (has_red) {
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      const uint32_t bytes = static_cast<uint32_t>(sizeof(double) * J * EP);
+      const double* src = P.Ftile + size_t(tile_idx) * J * EP;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes)
+                   : "memory");
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+              smem_u32(Fs)),
+          "l"(src), "r"(bytes), "r"(smem_u32(mbar))
+          : "memory");
+    }
+  }
+  // ---- additive terms per (epoch, realization): GWB grid interpolation at the epoch reference time and its
+  // slope, plus the ECORR draw of the epoch's bucket.  One work item = (epoch, 4 realizations), at most two per
+  // thread.  The scattered grid loads are issued here and consumed after the coefficient generation below.
+  constexpr int ADD_ITEMS = EP * RG / EPK_THREADS;  // 2
+  double g0[ADD_ITEMS][4], g1[ADD_ITEMS][4];
+  if (has_gwb) {
+#pragma unroll
+    for (int m = 0; m < ADD_ITEMS; ++m) {
+      const int idx = tid + m * EPK_THREADS;
+      if (idx < tile.n_ep * RG) {
+        const int e = idx / RG, rg = idx % RG;
+        const int j = P.ep_gidx[tile.ep_start + e];
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+          const int r = rg * 4 + l;
+          const double* Gr = P.G + size_t(r0 + (r < nr ? r : 0)) * P.g_ld + j;
+          g0[m][l] = __ldg(Gr);
+          g1[m][l] = __ldg(Gr + 1);
+        }
+      }
+    }
+  }
+  auto finish_add = [&]() {
+#pragma unroll
+    for (int m = 0; m < ADD_ITEMS; ++m) {
+      const int idx = tid + m * EPK_THREADS;
+      if (idx < tile.n_ep * RG) {
+        const int e = idx / RG, rg = idx % RG;
+        const int ge = tile.ep_start + e;
+        double add0[4] = {0.0, 0.0, 0.0, 0.0}, add1[4] = {0.0, 0.0, 0.0, 0.0};
+        if (has_gwb) {
+          const double gwt = P.ep_gw[ge], ginv = P.ep_ginv[ge];
+#pragma unroll
+          for (int l = 0; l < 4; ++l) {
+            if (rg * 4 + l < nr) {
+              const double dg = g1[m][l] - g0[m][l];
+              add0[l] = fma(gwt, dg, g0[m][l]);
+              add1[l] = dg * ginv;
+            }
+          }
+        }
+        if (has_ecorr) {
+          const double ec = P.ep_ecorr[ge];
+          if (INJECT) {
+            const size_t zo = P.psr_bucket_off[psr] + P.ep_bucket[ge];
+#pragma unroll
+            for (int l = 0; l < 4; ++l)
+              if (rg * 4 + l < nr) add0[l] += ec * P.zb[size_t(r0 + rg * 4 + l) * P.n_bucket_total + zo];
+          } else {
+            float n[4];
+            normals4(n, P.ep_bucket[ge], PTAR_K_ECORR, psr, rgroup0 + rg, K);
+#pragma unroll
+            for (int l = 0; l < 4; ++l) add0[l] += ec * static_cast<double>(n[l]);
+          }
+        }
+        double2* q = reinterpret_cast<double2*>(Add + (size_t(e) * RB + rg * 4) * 2);
+#pragma unroll
+        for (int l = 0; l < 4; ++l) q[l] = make_double2(add0[l], add1[l]);
+      }
+    }
+  };
+
+  // GEMM ownership (same split-K rule as gen_body): realization pair rp, epochs e0..e0+3, column slice ks
+  const int nsplit = tile.n_ep <= 16 ? 4 : (tile.n_ep <= 32 ? 2 : 1);
+  const int gthreads = EPK_THREADS / nsplit;
+  const int ks = tid / gthreads, tg = tid % gthreads;
+  const int rp = tg & 15;
+  const int e0 = (tg >> 4) * 4;
+  double acc[4][2][3];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int l = 0; l < 2; ++l) acc[i][l][0] = acc[i][l][1] = acc[i][l][2] = 0.0;
+
+  if (has_red) {
+    {  // coefficients and their first two time derivatives for 32 realizations (overlaps the bulk copy)
+      const double* scale = P.rn_scale + size_t(psr) * J;
+      const double* om = P.rn_omega + size_t(psr) * (J / 2);
+      const double sgn_even = P.rn_convention ? 1.0 : -1.0;
+      double* A0 = As;
+      double* A1 = As + size_t(J) * RB;
+      double* A2 = As + size_t(2) * J * RB;
+      for (int idx = tid; idx < (J / 2) * RG; idx += EPK_THREADS) {
+        const int k = idx / RG, rg = idx % RG;
+        const int je = 2 * k, jo = 2 * k + 1;
+        double ye[4], yo[4];
+        if (INJECT) {
+#pragma unroll
+          for (int l = 0; l < 4; ++l) {
+            const int r = rg * 4 + l;
+            const bool ok = r < nr;
+            const size_t zi = (size_t(r0 + (ok ? r : 0)) * P.n_psr + psr) * J;
+            ye[l] = ok ? P.zrn[zi + je] : 0.0;
+            yo[l] = ok ? P.zrn[zi + jo] : 0.0;
+          }
+        } else {
+          float n[4];
+          normals4(n, je, PTAR_K_RED, psr, rgroup0 + rg, K);
+#pragma unroll
+          for (int l = 0; l < 4; ++l) ye[l] = static_cast<double>(n[l]);
+          normals4(n, jo, PTAR_K_RED, psr, rgroup0 + rg, K);
+#pragma unroll
+          for (int l = 0; l < 4; ++l) yo[l] = static_cast<double>(n[l]);
+        }
+        const double se = scale[je], so = scale[jo], w = om[k];
+        const double h = -0.5 * w * w;
+        double ae[4], ao[4];
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+          ae[l] = se * ye[l];
+          ao[l] = so * yo[l];
+        }
+        auto put = [&](double* row, double v0, double v1, double v2, double v3) {
+          double2* q = reinterpret_cast<double2*>(row + rg * 4);
+          q[0] = make_double2(v0, v1);
+          q[1] = make_double2(v2, v3);
+        };
+        put(A0 + je * RB, ae[0], ae[1], ae[2], ae[3]);
+        put(A0 + jo * RB, ao[0], ao[1], ao[2], ao[3]);
+        const double s1 = sgn_even * w, s2 = -sgn_even * w;
+        put(A1 + je * RB, s1 * ao[0], s1 * ao[1], s1 * ao[2], s1 * ao[3]);
+        put(A1 + jo * RB, s2 * ae[0], s2 * ae[1], s2 * ae[2], s2 * ae[3]);
+        put(A2 + je * RB, h * ae[0], h * ae[1], h * ae[2], h * ae[3]);
+        put(A2 + jo * RB, h * ao[0], h * ao[1], h * ao[2], h * ao[3]);
+      }
+    }
+    if (has_add) finish_add();
+    __syncthreads();  // As (and Add, and thread 0's mbarrier init) visible
+    {
+      uint32_t done = 0;
+      while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(mbar))
+            : "memory");
+      }
+    }
+    if (e0 < tile.n_ep) {
+      const int jlo = (J * ks) / nsplit, jhi = (J * (ks + 1)) / nsplit;
+      auto gemm = [&](auto ND) {
+        constexpr int kNd = decltype(ND)::value;
+#pragma unroll 2
+        for (int j = jlo; j < jhi; ++j) {
+          const double2 f01 = *reinterpret_cast<const double2*>(Fs + j * EP + e0);
+          const double2 f23 = *reinterpret_cast<const double2*>(Fs + j * EP + e0 + 2);
+          const double f[4] = {f01.x, f01.y, f23.x, f23.y};
+#pragma unroll
+          for (int d = 0; d < kNd; ++d) {
+            const double2 a = *reinterpret_cast<const double2*>(As + (d * J + j) * RB + 2 * rp);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              acc[i][0][d] = fma(f[i], a.x, acc[i][0][d]);
+              acc[i][1][d] = fma(f[i], a.y, acc[i][1][d]);
+            }
+          }
+        }
+      };
+      if (nd >= 3) gemm(std::integral_constant<int, 3>{});
+      else if (nd == 2) gemm(std::integral_constant<int, 2>{});
+      else gemm(std::integral_constant<int, 1>{});
+    }
+    if (nsplit > 1) {
+      // split-K: groups ks >= 1 park their 24 partial sums in scratch[ks-1][q][tg] (over the dead operands)
+      __syncthreads();
+      double* scratch = Fs;
+      if (ks > 0) {
+        double* s = scratch + size_t(ks - 1) * 24 * gthreads + tg;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int l = 0; l < 2; ++l)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) s[((i * 2 + l) * 3 + d) * gthreads] = acc[i][l][d];
+      }
+      __syncthreads();
+      if (ks == 0) {
+        for (int g = 1; g < nsplit; ++g) {
+          const double* s = scratch + size_t(g - 1) * 24 * gthreads + tg;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int l = 0; l < 2; ++l)
+#pragma unroll
+              for (int d = 0; d < 3; ++d) acc[i][l][d] += s[((i * 2 + l) * 3 + d) * gthreads];
+        }
+      }
+    }
+  } else if (has_add) {
+    finish_add();
+    __syncthreads();  // Add visible
+  }
+  // ---- out: 6 coefficients per epoch (2 realizations x 3 orders) = 48 contiguous bytes of the Cbuf row the TOA
+  // kernel fetches with one bulk copy; the eight pair-threads of a 16-realization block cover 384 B of it.
+  const int chunk = 2 * blockIdx.x + (rp >> 3);
+  if (ks == 0 && chunk < n_chunks) {
+    const int rl = (2 * rp) & 15;
+    double* blockp = P.Cbuf + (size_t(tile.reserved) * n_chunks + size_t(chunk) * tile.n_ep) * CSS;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = e0 + i;
+      if (e < tile.n_ep) {
+        double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+        if (has_add) {
+          const double2* q = reinterpret_cast<const double2*>(Add + (size_t(e) * RB + 2 * rp) * 2);
+          const double2 t0 = q[0], t1 = q[1];
+          a00 = t0.x; a01 = t0.y; a10 = t1.x; a11 = t1.y;
+        }
+        double2* o = reinterpret_cast<double2*>(blockp + size_t(e) * CSS + rl * 3);
+        __stcg(o, make_double2(acc[i][0][0] + a00, acc[i][0][1] + a01));
+        __stcg(o + 1, make_double2(acc[i][0][2], acc[i][1][0] + a10));
+        __stcg(o + 2, make_double2(acc[i][1][1] + a11, acc[i][1][2]));
+        if (rl == 14) __stcg(o + 3, make_double2(0.0, 0.0));  // row padding (doubles 48, 49)
+      }
+    }
+  }
+}
+
 }  // namespace ptar

@@ -172,6 +172,54 @@ def test_shards_and_chunks_are_bitwise_reproducible():
     assert torch.equal(full.cpu(), h)
 
 
+@pytest.mark.parametrize("exact", [False, True])
+def test_two_kernel_schedule_is_bitwise_the_fused_generator(exact):
+    """epoch kernel (tile x 32 realizations, ptar.cu launch_epoch) + TOA kernel against the fused kernel: same
+    summation order, so every realization count (odd numbers of 16-realization blocks, partial blocks), the
+    Philox mode and the injected mode must agree bit for bit; signal subsets exercise the flag paths."""
+    import torch
+    from pta_replicator_b200.engine import PulsarBatch
+    _, spec = load_flags_case()
+    psrs = _psrs(spec)
+
+    def both(b, n, **kw):
+        b.split_epoch = False
+        b._job_cache_key = None
+        x = b.generate(n, **kw)
+        b.split_epoch = True
+        b._job_cache_key = None
+        y = b.generate(n, **kw)
+        b.split_epoch = False
+        b._job_cache_key = None
+        return x, y
+
+    b = _batch(psrs, spec, exact_epochs=exact)
+    for n in (1, 5, 16, 17, 33, 48, 70):
+        x, y = both(b, n, seed=11, real0=4)
+        assert torch.equal(x, y), n
+    st = b.compile()
+    R, P = 19, len(spec)
+    rng = np.random.default_rng(6)
+    inj = dict(z1=torch.from_numpy(rng.standard_normal((R, b.ld))), z2=torch.from_numpy(rng.standard_normal((R, b.ld))),
+               zb=torch.from_numpy(rng.standard_normal((R, st["n_bucket_total"]))),
+               zrn=torch.from_numpy(rng.standard_normal((R, P, 60))),
+               gwb_z=torch.from_numpy(rng.standard_normal((R, P, st["gwb_T_Jreal"]))))
+    x, y = both(b, R, inject=inj)
+    assert torch.equal(x, y)
+    # subsets: ECORR only (no GEMM), red noise only, GWB only
+    for which in ("ecorr", "red", "gwb"):
+        s = PulsarBatch(psrs, exact_epochs=exact)
+        for i in range(P):
+            if which == "ecorr":
+                s.set_ecorr(i, log10_ecorr=-6.3)
+            elif which == "red":
+                s.set_red(i, -13.5, 3.3, components=30)
+        if which == "gwb":
+            s.set_gwb(-14.0, 4.0)
+        x, y = both(s, 21, seed=2)
+        assert torch.equal(x, y) and float(x.abs().max()) > 0, which
+
+
 def test_ragged_realization_counts():
     """nreal not a multiple of the Philox group (4), the CTA chunk (16) or the GWB chunk: a prefix of a
     longer run, bit for bit; single-pulsar / single-signal batches; a chunk that is not a multiple of 16."""
