@@ -16,6 +16,8 @@
  *   ptar_gwb_synth         sqrt(C) scale, Hermitian pack, ifft, crop    red_noise.py:269-285
  *   ptar_cgw_delay         add_cgw arithmetic                           deterministic.py:98-163
  *   ptar_cw_catalog        loop_over_CWs[_parallel] (numba)             deterministic.py:321-561
+ *   ptar_burst_delay       add_burst polarisation mix                   deterministic.py:771-780
+ *   ptar_memory_delay      add_gw_memory ramp                           deterministic.py:864-873
  *   ptar_generate          efac/equad draw                              white_noise.py:105-109
  *                          U @ (ecorr*z)                                white_noise.py:182
  *                          F @ (sqrt(prior)*z)                          red_noise.py:126-128
@@ -146,6 +148,17 @@ int ptar_cgw_delay(double* out, const double* t, const int32_t* psr_of_toa, cons
 int ptar_cw_catalog(double* out, const double* t, int64_t n_toa, const double* phat_host, const double* cat,
                     int64_t n_src, double pdist_kpc, double pphase, int use_pphase, int mode, int psr_term,
                     int accumulate, double* pre, double* partial, int n_slices, void* stream);
+
+/* Burst of arbitrary waveform (add_burst, deterministic.py:718-793).  hplus / hcross are the
+ * caller's waveform callables sampled at t = mjd*86400 - tref (the callables are Python objects in the reference too);
+ * fplus / fcross the antenna pattern (:757-759).  out[i] (+)= -fplus (h+ cos2psi - hx sin2psi) - fcross (h+ sin2psi +
+ * hx cos2psi), every product rounded separately like numpy. */
+int ptar_burst_delay(double* out, const double* hplus, const double* hcross, double fplus, double fcross, double cos2psi,
+                     double sin2psi, int accumulate, int64_t n, void* stream);
+
+/* Burst with memory (add_gw_memory, deterministic.py:822-884): out[i] (+)= t[i] < t0 ? 0 : amp (t[i] - t0), with
+ * t = mjd*86400, t0 = t0_mjd*86400 and amp = (cos(2 pol) fplus + sin(2 pol) fcross) * strain. */
+int ptar_memory_delay(double* out, const double* t, double amp, double t0, int accumulate, int64_t n, void* stream);
 
 /* Zm[p][r][j] = sum_q M[p][q] z[r][q][j]  (output pulsar-major: [n_psr][nreal][J]).  z is read from
  * zin[r][q][j] (parity) or drawn from Philox (zin == NULL; stream PTAR_K_GWB).  M is n_psr x n_psr lower

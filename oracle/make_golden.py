@@ -254,6 +254,32 @@ def make_catalog(ref):
     np.savez(os.path.join(GOLD, "ref_catalog.npz"), **store)
 
 
+def make_f4(ref):
+    """``add_burst`` (deterministic.py:718-793, with and without ``remove_quad``), ``add_noise_transient`` (:796-819)
+    and ``add_gw_memory`` (:822-884) on the 4 synthetic pulsars; the waveforms live in tests/fixtures.py."""
+    import importlib.util
+    # by path: the reference tree on sys.path has a ``tests`` package of its own
+    sp = importlib.util.spec_from_file_location("ptar_test_fixtures", os.path.join(os.path.dirname(GOLD), "fixtures.py"))
+    fx = importlib.util.module_from_spec(sp)
+    sp.loader.exec_module(fx)
+    spec = synth_flag_pulsars()
+    store = {}
+    for i, s in enumerate(spec):
+        def fresh():
+            return refstubs.StubPulsar(s["name"], s["loc"], s["mjd"].astype(np.longdouble), s["err_us"], s["flags"])
+        for tag, quad in (("burst", False), ("burstq", True)):
+            p = fresh()
+            ref.deterministic.add_burst(p, 1.1, 4.0, fx.burst_plus, fx.burst_cross, psi=0.7, tref=fx.F4_TREF, remove_quad=quad)
+            store[f"{tag}_{i}"] = p.signal_seconds(f"{p.name}_burst")
+        p = fresh()
+        ref.deterministic.add_noise_transient(p, fx.transient_waveform, tref=fx.F4_TREF)
+        store[f"transient_{i}"] = p.signal_seconds(f"{p.name}_noise_transient")
+        p = fresh()
+        ref.deterministic.add_gw_memory(p, 3.0e-14, 0.9, 2.2, 0.4, fx.F4_T0_MJD)
+        store[f"memory_{i}"] = p.signal_seconds(f"{p.name}_gw_memory")
+    np.savez(os.path.join(GOLD, "ref_f4.npz"), **store)
+
+
 def make_orf(ref):
     rng = np.random.default_rng(3)
     n = 9
@@ -281,6 +307,7 @@ def main():
     make_flags(ref)
     make_orf(ref)
     make_catalog(ref)
+    make_f4(ref)
     print("golden fixtures written to", GOLD)
 
 

@@ -279,6 +279,49 @@ def cw_catalog(mjd, loc, cat, **kw):
     return out
 
 
+# --------------------------------------------------------------------------- bursts, transients, memory
+def antenna(loc, gwtheta, gwphi):
+    """(fplus, fcross) as in deterministic.py:733-759 / :837-862 for RAJ/DECJ positions."""
+    ct, cp, st, sp = np.cos(gwtheta), np.cos(gwphi), np.sin(gwtheta), np.sin(gwphi)
+    m = np.array([sp, -cp, 0.0])
+    n = np.array([-ct * cp, -ct * sp, st])
+    om = np.array([-st * cp, -st * sp, -ct])
+    ptheta = np.pi / 2 - loc["DECJ"] * np.pi / 180.0
+    pphi = loc["RAJ"] * np.pi / 12.0
+    phat = np.array([np.sin(ptheta) * np.cos(pphi), np.sin(ptheta) * np.sin(pphi), np.cos(ptheta)])
+    fplus = 0.5 * (np.dot(m, phat) ** 2 - np.dot(n, phat) ** 2) / (1 + np.dot(om, phat))
+    fcross = (np.dot(m, phat) * np.dot(n, phat)) / (1 + np.dot(om, phat))
+    return fplus, fcross
+
+
+def burst(mjd, loc, gwtheta, gwphi, waveform_plus, waveform_cross, psi=0.0, tref=0, remove_quad=False):
+    """deterministic.py:761-780: elliptically polarised burst, optional quadratic removal (np.polyfit)."""
+    fplus, fcross = antenna(loc, gwtheta, gwphi)
+    toas = np.asarray(mjd, float) * 86400 - tref
+    hplus, hcross = waveform_plus(toas), waveform_cross(toas)
+    rplus = hplus * np.cos(2 * psi) - hcross * np.sin(2 * psi)
+    rcross = hplus * np.sin(2 * psi) + hcross * np.cos(2 * psi)
+    res = -fplus * rplus - fcross * rcross
+    if remove_quad:
+        pp = np.polyfit(toas, res, 2)
+        res = res - pp[0] * toas ** 2 - pp[1] * toas - pp[2]
+    return res
+
+
+def noise_transient(mjd, waveform, tref=0):
+    """deterministic.py:805-810."""
+    return waveform(np.asarray(mjd, float) * 86400 - tref)
+
+
+def gw_memory(mjd, loc, strain, gwtheta, gwphi, bwm_pol, t0_mjd):
+    """deterministic.py:864-873: ramp pol * strain * (t - t0) after the burst epoch."""
+    fplus, fcross = antenna(loc, gwtheta, gwphi)
+    pol = np.cos(2 * bwm_pol) * fplus + np.sin(2 * bwm_pol) * fcross
+    toas = np.asarray(mjd, float) * 86400
+    t0 = t0_mjd * 86400
+    return np.where(toas < t0, 0.0, pol * strain * (toas - t0))
+
+
 # --------------------------------------------------------------------------- whole recipes
 def weighted_mean_residual(delay, err):
     """residual formation without PINT."""

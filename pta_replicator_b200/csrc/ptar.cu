@@ -193,6 +193,28 @@ __global__ void cw_reduce_kernel(double* __restrict__ out, const double* __restr
   out[i] = accumulate ? out[i] + a : a;
 }
 
+// deterministic.py:771-780: elliptically polarised burst from the two waveform samples of each TOA.  The products are
+// rounded one by one (no FMA contraction) so the result is the reference's bit for bit.
+__global__ void burst_kernel(double* __restrict__ out, const double* __restrict__ hplus, const double* __restrict__ hcross,
+                             double fplus, double fcross, double c2, double s2, int accumulate, int64_t n) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double hp = hplus[i], hx = hcross[i];
+  const double rplus = __dsub_rn(__dmul_rn(hp, c2), __dmul_rn(hx, s2));
+  const double rcross = __dadd_rn(__dmul_rn(hp, s2), __dmul_rn(hx, c2));
+  const double res = __dsub_rn(__dmul_rn(-fplus, rplus), __dmul_rn(fcross, rcross));
+  out[i] = accumulate ? out[i] + res : res;
+}
+
+// deterministic.py:868-872: burst with memory, a ramp after the burst epoch.
+__global__ void memory_kernel(double* __restrict__ out, const double* __restrict__ t, double amp, double t0, int accumulate,
+                              int64_t n) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double res = t[i] < t0 ? 0.0 : __dmul_rn(amp, __dsub_rn(t[i], t0));
+  out[i] = accumulate ? out[i] + res : res;
+}
+
 __global__ void philox_normals_kernel(float* __restrict__ out, int kind, int psr, int64_t realization, int64_t idx0,
                                       int64_t n, uint64_t seed) {
   const int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -285,6 +307,23 @@ int ptar_cgw_delay(double* out, const double* t, const int32_t* psr_of_toa, cons
   cgw_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       out, t, psr_of_toa, psr_par, src, mode, psr_term, accumulate, n);
   return check_launch("ptar_cgw_delay");
+}
+
+int ptar_burst_delay(double* out, const double* hplus, const double* hcross, double fplus, double fcross, double cos2psi,
+                     double sin2psi, int accumulate, int64_t n, void* stream) {
+  if (!out || !hplus || !hcross || n < 0) return fail(-1, "ptar_burst_delay: bad argument%s");
+  if (n == 0) return 0;
+  burst_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      out, hplus, hcross, fplus, fcross, cos2psi, sin2psi, accumulate, n);
+  return check_launch("ptar_burst_delay");
+}
+
+int ptar_memory_delay(double* out, const double* t, double amp, double t0, int accumulate, int64_t n, void* stream) {
+  if (!out || !t || n < 0) return fail(-1, "ptar_memory_delay: bad argument%s");
+  if (n == 0) return 0;
+  memory_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, t, amp, t0,
+                                                                                                     accumulate, n);
+  return check_launch("ptar_memory_delay");
 }
 
 int ptar_cw_catalog(double* out, const double* t, int64_t n_toa, const double* phat_host, const double* cat, int64_t n_src,

@@ -1,6 +1,6 @@
-"""Deterministic signals -- drop-in for ``add_cgw`` of
-``/root/reference/pta_replicator/deterministic.py:13-185`` (the only deterministic signal on the
-hot path; catalogs, bursts and memory are "next" rows f1/f4).
+"""Deterministic signals -- drop-ins for ``add_cgw`` (``/root/reference/pta_replicator/deterministic.py:13-185``,
+the deterministic signal on the hot path), ``add_catalog_of_cws`` (:188-561, row f1) and
+``add_burst`` / ``add_noise_transient`` / ``add_gw_memory`` (:718-884, row f4).
 """
 from __future__ import annotations
 
@@ -72,3 +72,79 @@ def add_catalog_of_cws(psr, gwtheta_list, gwphi_list, mc_list, dist_list, fgw_li
                               "phase_approx": phase_approx, "tref": tref}, dt)
     psr.toas.adjust_TOAs(dt.to("day"))
     psr.update_residuals()
+
+
+def _antenna(psr, gwtheta, gwphi):
+    """(fplus, fcross) of deterministic.py:733-759 (Sesana et al. 2010 / Ellis et al. 2012 conventions)."""
+    from . import orf as orf_mod
+    cgt, cgp, sgt, sgp = np.cos(gwtheta), np.cos(gwphi), np.sin(gwtheta), np.sin(gwphi)
+    m = np.array([sgp, -cgp, 0.0])
+    n = np.array([-cgt * cgp, -cgt * sgp, sgt])
+    om = np.array([-sgt * cgp, -sgt * sgp, -cgt])
+    radec = orf_mod.psrlocs_from_pulsars([psr])[0]
+    ptheta, pphi = np.pi / 2 - radec[1], radec[0]
+    phat = np.array([np.sin(ptheta) * np.cos(pphi), np.sin(ptheta) * np.sin(pphi), np.cos(ptheta)])
+    fplus = 0.5 * (np.dot(m, phat) ** 2 - np.dot(n, phat) ** 2) / (1 + np.dot(om, phat))
+    fcross = (np.dot(m, phat) * np.dot(n, phat)) / (1 + np.dot(om, phat))
+    return float(fplus), float(fcross)
+
+
+def _inject(psr, name, params, seconds):
+    dt = TimeArray(np.asarray(seconds, dtype=np.float64), "s")
+    psr.update_added_signals(name, params, dt)
+    psr.toas.adjust_TOAs(dt.to("day"))
+    psr.update_residuals()
+
+
+def add_burst(psr, gwtheta, gwphi, waveform_plus, waveform_cross, psi=0.0, tref=0, remove_quad=False, signal_name="burst"):
+    """GW burst of arbitrary waveform with elliptical polarisation -- drop-in for ``add_burst``
+    (deterministic.py:718-793).  The two waveform callables are evaluated on the host (they are the caller's Python
+    functions of ``t - tref`` [s], as in the reference); the polarisation mix and antenna projection run in
+    ``ptar_burst_delay``.  ``remove_quad`` fits the quadratic out with ``np.polyfit`` like the reference (:777-779)."""
+    import torch
+
+    from . import _cabi
+    dev = _cabi.require_cuda()
+    fplus, fcross = _antenna(psr, gwtheta, gwphi)
+    toas = np.asarray(psr.toas.get_mjds().value, dtype=np.float64) * 86400 - tref
+    def sample(w):  # a scalar-valued callable broadcasts like numpy would in the reference
+        return torch.from_numpy(np.array(np.broadcast_to(np.asarray(w(toas), dtype=np.float64), toas.shape))).to(dev)
+
+    hp, hx = sample(waveform_plus), sample(waveform_cross)
+    out = torch.empty(len(toas), dtype=torch.float64, device=dev)
+    _cabi.check(_cabi.lib().ptar_burst_delay(out.data_ptr(), hp.data_ptr(), hx.data_ptr(), fplus, fcross, float(np.cos(2 * psi)),
+                                             float(np.sin(2 * psi)), 0, len(toas), _cabi.current_stream()), "ptar_burst_delay")
+    res = out.cpu().numpy()
+    if remove_quad:
+        pp = np.polyfit(toas, res, 2)
+        res = res - pp[0] * toas ** 2 - pp[1] * toas - pp[2]
+    _inject(psr, "{}_".format(psr.name) + signal_name,
+            {"gwtheta": gwtheta, "gwphi": gwphi, "waveform_plus": waveform_plus, "waveform_cross": waveform_cross, "psi": psi,
+             "tref": tref, "remove_quad": remove_quad}, res)
+
+
+def add_noise_transient(psr, waveform, tref=0, signal_name="noise_transient"):
+    """Incoherent transient of arbitrary waveform in one pulsar -- drop-in for ``add_noise_transient``
+    (deterministic.py:796-819).  The delay IS the caller's callable sampled at ``t - tref``; there is no arithmetic to
+    move to the device, so this is ledger bookkeeping only."""
+    toas = np.asarray(psr.toas.get_mjds().value, dtype=np.float64) * 86400 - tref
+    res = np.array(np.broadcast_to(np.asarray(waveform(toas), dtype=np.float64), toas.shape))
+    _inject(psr, "{}_".format(psr.name) + signal_name, {"waveform": waveform, "tref": tref}, res)
+
+
+def add_gw_memory(psr, strain, gwtheta, gwphi, bwm_pol, t0_mjd, signal_name="gw_memory"):
+    """Burst with memory -- drop-in for ``add_gw_memory`` (deterministic.py:822-884): a ramp
+    ``pol * strain * (t - t0)`` after the burst epoch, evaluated by ``ptar_memory_delay``."""
+    import torch
+
+    from . import _cabi
+    dev = _cabi.require_cuda()
+    fplus, fcross = _antenna(psr, gwtheta, gwphi)
+    pol = np.cos(2 * bwm_pol) * fplus + np.sin(2 * bwm_pol) * fcross
+    toas = np.asarray(psr.toas.get_mjds().value, dtype=np.float64) * 86400
+    t_d = torch.from_numpy(np.ascontiguousarray(toas)).to(dev)
+    out = torch.empty(len(toas), dtype=torch.float64, device=dev)
+    _cabi.check(_cabi.lib().ptar_memory_delay(out.data_ptr(), t_d.data_ptr(), float(pol * strain), float(t0_mjd * 86400), 0,
+                                              len(toas), _cabi.current_stream()), "ptar_memory_delay")
+    _inject(psr, "{}_".format(psr.name) + signal_name,
+            {"strain": strain, "gwtheta": gwtheta, "gwphi": gwphi, "bwm_pol": bwm_pol, "t0_mjd": t0_mjd}, out.cpu().numpy())

@@ -38,3 +38,20 @@ def load_small_case():
 def rel_rms(a, b):
     """max|a-b| / rms(b)."""
     return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / np.sqrt(np.mean(np.square(b))))
+
+
+# Waveforms of the burst / transient cases (shared by oracle/make_golden.py and the tests; t = TOA - tref in seconds)
+F4_TREF = 55000.0 * 86400.0
+F4_T0_MJD = 55800.0
+
+
+def burst_plus(t):
+    return 2.0e-7 * np.exp(-0.5 * ((t - 3.0e7) / 6.0e6) ** 2) * np.sin(2 * np.pi * t / 2.5e7)
+
+
+def burst_cross(t):
+    return 1.3e-7 * np.exp(-0.5 * ((t - 3.4e7) / 9.0e6) ** 2) * np.cos(2 * np.pi * t / 3.1e7)
+
+
+def transient_waveform(t):
+    return 5.0e-7 * np.where(t > 1.0e7, np.exp(-(t - 1.0e7) / 4.0e7), 0.0)

@@ -173,3 +173,19 @@ def test_cw_catalog_oracle_against_reference_numba_loops(tag):
     for i, s in enumerate(spec):
         got = O.cw_catalog(s["mjd"], s["loc"], cat, tref=53000 * 86400, **CAT_VARIANTS[tag])
         assert rel_rms(got, c[f"cat_{tag}_{i}"]) < tol
+
+
+def test_burst_transient_memory_against_reference_outputs():
+    """Rows f4 of SURVEY.md section 8: the restatements of add_burst / add_noise_transient / add_gw_memory against
+    the unmodified reference run on the 4 synthetic pulsars (tests/golden/ref_f4.npz, oracle/make_golden.py:make_f4)."""
+    from tests import fixtures as fx
+    z = np.load(os.path.join(fx.GOLD, "ref_f4.npz"))
+    _, spec = fx.load_flags_case()
+    for i, s in enumerate(spec):
+        for tag, quad in (("burst", False), ("burstq", True)):
+            got = O.burst(s["mjd"], s["loc"], 1.1, 4.0, fx.burst_plus, fx.burst_cross, psi=0.7, tref=fx.F4_TREF, remove_quad=quad)
+            assert fx.rel_rms(got, z[f"{tag}_{i}"]) < 1e-12, (tag, i)
+        assert np.array_equal(O.noise_transient(s["mjd"], fx.transient_waveform, tref=fx.F4_TREF), z[f"transient_{i}"])
+        got = O.gw_memory(s["mjd"], s["loc"], 3.0e-14, 0.9, 2.2, 0.4, fx.F4_T0_MJD)
+        assert fx.rel_rms(got, z[f"memory_{i}"]) < 1e-13, i
+        assert (z[f"memory_{i}"] == 0).any() and (z[f"memory_{i}"] != 0).any()
