@@ -254,14 +254,38 @@ def make_catalog(ref):
     np.savez(os.path.join(GOLD, "ref_catalog.npz"), **store)
 
 
-def make_f4(ref):
-    """``add_burst`` (deterministic.py:718-793, with and without ``remove_quad``), ``add_noise_transient`` (:796-819)
-    and ``add_gw_memory`` (:822-884) on the 4 synthetic pulsars; the waveforms live in tests/fixtures.py."""
+def _fixtures_module():
     import importlib.util
     # by path: the reference tree on sys.path has a ``tests`` package of its own
     sp = importlib.util.spec_from_file_location("ptar_test_fixtures", os.path.join(os.path.dirname(GOLD), "fixtures.py"))
     fx = importlib.util.module_from_spec(sp)
     sp.loader.exec_module(fx)
+    return fx
+
+
+def make_outliers(ref):
+    """``add_gwb_plus_outlier_cws`` (deterministic.py:565-715) on the 4 synthetic pulsars with a 4000-sample population,
+    3 outliers per bin.  holodeck / astropy.constants are stand-ins (oracle/refstubs.py); everything else is the
+    unmodified reference: binning, ranking, free spectrum, add_gwb(userSpec), the global-stream draws, the catalog."""
+    fx = _fixtures_module()
+    vals, weights, fobs, T_obs = fx.outlier_population()
+    spec = synth_flag_pulsars()
+    psrs = [refstubs.StubPulsar(s["name"], s["loc"], s["mjd"].astype(np.longdouble), s["err_us"], s["flags"]) for s in spec]
+    ret = ref.deterministic.add_gwb_plus_outlier_cws(psrs, vals, weights, fobs, T_obs, outlier_per_bin=3, seed=4242)
+    names = ("f_centers", "free_spec", "outlier_fo", "outlier_hs", "outlier_mc", "outlier_dl", "gwthetas", "gwphis", "phases",
+             "psis", "incs")
+    store = {k: np.asarray(v) for k, v in zip(names, ret)}
+    for i, p in enumerate(psrs):
+        store[f"gwb_{i}"] = p.signal_seconds(f"{p.name}_gwb")
+        store[f"cw_{i}"] = p.signal_seconds(f"{p.name}_cw_catalog")
+    assert len(store["outlier_fo"]) == 18
+    np.savez(os.path.join(GOLD, "ref_outliers.npz"), **store)
+
+
+def make_f4(ref):
+    """``add_burst`` (deterministic.py:718-793, with and without ``remove_quad``), ``add_noise_transient`` (:796-819)
+    and ``add_gw_memory`` (:822-884) on the 4 synthetic pulsars; the waveforms live in tests/fixtures.py."""
+    fx = _fixtures_module()
     spec = synth_flag_pulsars()
     store = {}
     for i, s in enumerate(spec):
@@ -308,6 +332,7 @@ def main():
     make_orf(ref)
     make_catalog(ref)
     make_f4(ref)
+    make_outliers(ref)
     print("golden fixtures written to", GOLD)
 
 

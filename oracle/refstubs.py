@@ -106,6 +106,39 @@ def _module(name, **attrs):
     return m
 
 
+# ---- stand-ins for the four holodeck functions / two astropy constants used by add_gwb_plus_outlier_cws
+# (deterministic.py:614-631).  holodeck is not installed: these restate the published definitions (the strain
+# formula is the one quoted at deterministic.py:636-637; flat LambdaCDM with holodeck's default WMAP9 parameters)
+# so that the UNMODIFIED reference function can run and pin the partition / draw-order / injection logic.
+_H_G, _H_C = 6.6743e-8, 2.99792458e10
+_H_MSOL, _H_PC = 1.988409870698051e33, 3.0856775814913674e18
+_H_H0, _H_OM = 69.32, 0.2865
+
+
+def _h_m1m2_from_mtmr(mt, mr):
+    mt, mr = np.asarray(mt, dtype=float), np.asarray(mr, dtype=float)
+    m1 = mt / (1.0 + mr)
+    return m1, mt - m1
+
+
+def _h_chirp_mass(m1, m2):
+    return np.power(m1 * m2, 3.0 / 5.0) / np.power(m1 + m2, 1.0 / 5.0)
+
+
+def _h_gw_strain_source(mchirp, dcom, freq_rest_orb):
+    return (8.0 / np.sqrt(10.0)) * np.power(_H_G * mchirp, 5.0 / 3.0) * np.power(2.0 * np.pi * freq_rest_orb, 2.0 / 3.0) / (
+        _H_C ** 4 * dcom)
+
+
+def _h_z_to_dcom(z):
+    x, w = np.polynomial.legendre.leggauss(64)
+    z = np.atleast_1d(np.asarray(z, dtype=float))
+    h0 = _H_H0 * 1.0e5 / (1.0e6 * _H_PC)
+    zz = 0.5 * z[:, None] * (x[None, :] + 1.0)
+    integrand = 1.0 / np.sqrt(_H_OM * (1.0 + zz) ** 3 + (1.0 - _H_OM))
+    return (_H_C / h0) * 0.5 * z * np.sum(w[None, :] * integrand, axis=1)
+
+
 def install():
     """Install the stubs and put the reference on ``sys.path``.  Idempotent."""
     if "pta_replicator" in sys.modules and getattr(sys.modules["pta_replicator"], "_ptar_stubbed", False):
@@ -127,9 +160,12 @@ def install():
     epulsar = _module("enterprise.pulsar", Pulsar=_Dummy)
     _module("enterprise", pulsar=epulsar)
     _module("ephem")
-    hutils = _module("holodeck.utils")
-    hcosmo = _module("holodeck.cosmo")
+    hutils = _module("holodeck.utils", m1m2_from_mtmr=_h_m1m2_from_mtmr, chirp_mass=_h_chirp_mass,
+                     gw_strain_source=_h_gw_strain_source)
+    hcosmo = _module("holodeck.cosmo", z_to_dcom=_h_z_to_dcom)
     _module("holodeck", utils=hutils, cosmo=hcosmo)
+    cgs = lambda v: types.SimpleNamespace(cgs=types.SimpleNamespace(value=v))  # noqa: E731
+    sys.modules["astropy"].constants = _module("astropy.constants", pc=cgs(_H_PC), M_sun=cgs(_H_MSOL))
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
     pkg = importlib.import_module("pta_replicator")

@@ -10,7 +10,7 @@ from .simulate import (SimulatedPulsar, load_from_directories, load_pulsar, make
 __all__ = ["SimulatedPulsar", "load_pulsar", "load_from_directories", "simulate_pulsar", "make_ideal",
            "pulsar_from_arrays", "add_measurement_noise", "add_jitter", "add_efac", "add_ecorr",
            "add_red_noise", "add_gwb", "add_cgw", "add_catalog_of_cws", "add_burst", "add_noise_transient",
-           "add_gw_memory", "PulsarBatch"]
+           "add_gw_memory", "add_gwb_plus_outlier_cws", "PulsarBatch"]
 
 
 def __getattr__(name):  # lazy: keeps `import pta_replicator_b200` free of torch
@@ -20,7 +20,8 @@ def __getattr__(name):  # lazy: keeps `import pta_replicator_b200` free of torch
     if name in ("add_red_noise", "add_gwb", "create_fourier_design_matrix_red"):
         from . import red_noise
         return getattr(red_noise, name)
-    if name in ("add_cgw", "add_catalog_of_cws", "add_burst", "add_noise_transient", "add_gw_memory"):
+    if name in ("add_cgw", "add_catalog_of_cws", "add_burst", "add_noise_transient", "add_gw_memory",
+                "add_gwb_plus_outlier_cws"):
         from . import deterministic
         return getattr(deterministic, name)
     if name == "PulsarBatch":

@@ -148,3 +148,29 @@ def add_gw_memory(psr, strain, gwtheta, gwphi, bwm_pol, t0_mjd, signal_name="gw_
                                               len(toas), _cabi.current_stream()), "ptar_memory_delay")
     _inject(psr, "{}_".format(psr.name) + signal_name,
             {"strain": strain, "gwtheta": gwtheta, "gwphi": gwphi, "bwm_pol": bwm_pol, "t0_mjd": t0_mjd}, out.cpu().numpy())
+
+
+def add_gwb_plus_outlier_cws(psrs, vals, weights, fobs, T_obs, outlier_per_bin=100, seed=None):
+    """Realistic data sets from a binary population -- drop-in for ``add_gwb_plus_outlier_cws``
+    (deterministic.py:565-715; Becsy, Cornish & Kelley 2022): the loudest ``outlier_per_bin`` binaries of every
+    frequency bin are injected one by one (``add_catalog_of_cws`` -> ``ptar_cw_catalog``), the rest as a GWB with a
+    free spectrum (``add_gwb(userSpec=...)`` -> the GWB kernels).  ``vals`` = [Mtot [g], q, z, f_obs [Hz]] per
+    population sample, ``weights`` = binaries per sample, ``fobs`` = bin edges [Hz], ``T_obs`` [s]; the holodeck
+    helpers are restated in ``population.py``.  Same draw order from the global ``np.random`` stream and the same
+    return tuple as the reference."""
+    from .population import partition_population
+    from .red_noise import add_gwb
+    f_centers, free_spec, outlier_fo, outlier_hs, outlier_mc, outlier_dl = partition_population(
+        vals, weights, fobs, T_obs, outlier_per_bin)
+    add_gwb(psrs, None, None, userSpec=np.array([f_centers, np.sqrt(free_spec)]).T, howml=10, seed=seed)
+    n_cw = outlier_hs.shape[0]
+    gwthetas = np.arccos(np.random.uniform(low=-1.0, high=1.0, size=n_cw))       # deterministic.py:693-697
+    gwphis = np.random.uniform(low=0.0, high=2 * np.pi, size=n_cw)
+    phases = np.random.uniform(low=0.0, high=2 * np.pi, size=n_cw)
+    psis = np.random.uniform(low=0.0, high=np.pi, size=n_cw)
+    incs = np.arccos(np.random.uniform(low=-1.0, high=1.0, size=n_cw))
+    for psr in psrs:
+        add_catalog_of_cws(psr, gwtheta_list=gwthetas, gwphi_list=gwphis, mc_list=outlier_mc, dist_list=outlier_dl,
+                           fgw_list=outlier_fo, phase0_list=phases, psi_list=psis, inc_list=incs, pdist=1.0, pphase=None,
+                           psrTerm=True, evolve=True, phase_approx=False, tref=53000 * 86400)
+    return f_centers, free_spec, outlier_fo, outlier_hs, outlier_mc, outlier_dl, gwthetas, gwphis, phases, psis, incs

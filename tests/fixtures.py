@@ -55,3 +55,14 @@ def burst_cross(t):
 
 def transient_waveform(t):
     return 5.0e-7 * np.where(t > 1.0e7, np.exp(-(t - 1.0e7) / 4.0e7), 0.0)
+
+
+def outlier_population(seed=77, n=4000):
+    """Synthetic SMBHB population in holodeck's layout: vals = [Mtot [g], q, z, f_obs [Hz]], weights, bin edges."""
+    msol = 1.988409870698051e33
+    rng = np.random.default_rng(seed)
+    fobs = np.arange(1, 8) / (16.03 * 365.25 * 86400.0)              # 6 bins at multiples of 1/T
+    vals = np.stack([10 ** rng.uniform(8.5, 10.3, n) * msol, rng.uniform(0.1, 1.0, n), 10 ** rng.uniform(-1.5, 0.3, n),
+                     rng.uniform(fobs[0], fobs[-1], n)])
+    weights = 10 ** rng.uniform(-1.0, 2.5, n)
+    return vals, weights, fobs, 16.03 * 365.25 * 86400.0

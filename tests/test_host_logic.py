@@ -211,3 +211,28 @@ def test_shard_bounds_cover_everything():
                 assert s % 4 == 0 or c == 0
                 pos = s + c if c else pos
             assert sum(c for _, c in got) == nreal
+
+
+def test_population_partition_matches_the_reference_function():
+    """the realization-independent half of add_gwb_plus_outlier_cws (deterministic.py:616-689)
+    against the arrays the unmodified reference returned (tests/golden/ref_outliers.npz; holodeck helpers stood in by
+    the same published formulas on both sides, see population.py)."""
+    import os
+
+    from pta_replicator_b200.population import partition_population, z_to_dcom
+    from tests import fixtures as fx
+    z = np.load(os.path.join(fx.GOLD, "ref_outliers.npz"))
+    vals, weights, fobs, T_obs = fx.outlier_population()
+    f_centers, free_spec, o_fo, o_hs, o_mc, o_dl = partition_population(vals, weights, fobs, T_obs, outlier_per_bin=3)
+    for got, key in ((f_centers, "f_centers"), (free_spec, "free_spec"), (o_fo, "outlier_fo"), (o_hs, "outlier_hs"),
+                     (o_mc, "outlier_mc"), (o_dl, "outlier_dl")):
+        assert np.array_equal(got, z[key]), key
+    # per bin the kept sources are the loudest, in descending order
+    assert all(np.all(np.diff(o_hs[3 * k:3 * k + 3]) <= 0) for k in range(6))
+    # fewer members than slots: empty slots are dropped, nothing is left for the free spectrum
+    f2, fs2, fo2, hs2, _, _ = partition_population(vals[:, :5], weights[:5], fobs, T_obs, outlier_per_bin=3)
+    assert len(fo2) == 5 and np.all(fs2 == 1e-100)
+    # comoving distance: Hubble law at low z, monotonic, ~ 3.3 Gpc at z = 1 for this cosmology
+    d = z_to_dcom(np.array([1e-3, 0.5, 1.0]))
+    mpc = 3.0856775814913674e24
+    assert abs(d[0] / mpc - 1e-3 * 2.99792458e5 / 69.32) < 2e-3 and d[0] < d[1] < d[2] and 3200 < d[2] / mpc < 3500
