@@ -6,7 +6,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
-enum Op { WIDE, MHI, MLO, MUFU, CVT, DFMA, LOP, FMUL, NONE };
+enum Op { WIDE, MHI, MLO, MUFU, CVT, DFMA, LOP, FMUL, NONE, DMMA, LDS };
 
 template <int OP>
 __device__ __forceinline__ void op(uint32_t& a, uint32_t& b, float& f, double& d) {
@@ -28,12 +28,20 @@ __device__ __forceinline__ void op(uint32_t& a, uint32_t& b, float& f, double& d
     asm volatile("add.u32 %0, %0, %1; xor.b32 %1, %1, %0;" : "+r"(b), "+r"(a));  // IADD3 + LOP3 (both alu pipe)
   } else if (OP == FMUL) {
     asm volatile("mul.ftz.f32 %0, %0, %0;" : "+f"(f));
+  } else if (OP == DMMA) {  // D(8x8) = A(8x4) B(4x8) + C on the FP64 tensor path: 256 FMA per warp instruction
+    asm volatile("{.reg .f64 c1; mov.f64 c1, %0; mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, c1}, {%1}, {%2}, {%0, c1};}"
+                 : "+d"(d) : "d"(1.0e-3), "d"(1.0e-3));
+  } else if (OP == LDS) {   // 128-bit shared load whose address depends on the previous one
+    asm volatile("{.reg .b32 x, y, z, w; ld.shared.v4.b32 {x, y, z, w}, [%0]; and.b32 %0, x, 0x3ff0;}" : "+r"(a));
   }
 }
 
 template <int A, int B>
 __global__ void __launch_bounds__(256, 4) k(float* out, int iters) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ uint4 sm[1024];
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) sm[i] = make_uint4((i * 16) & 0x3ff0, 0, 0, 0);
+  __syncthreads();
   uint32_t a[4], b[4], a2[4], b2[4];
   float f[4], g[4];
   double d[4], e[4];
@@ -100,6 +108,14 @@ int main() {
   run<MHI, MLO>("IMAD.HI + IMAD(lo)", out);
   run<MHI, MUFU>("IMAD.HI + MUFU", out);
   run<DFMA, LOP>("DFMA + IADD3+LOP3", out);
+  run<DMMA, NONE>("DMMA.884", out);
+  run<DMMA, WIDE>("DMMA + IMAD.WIDE", out);
+  run<DMMA, MUFU>("DMMA + MUFU", out);
+  run<DMMA, LOP>("DMMA + IADD3+LOP3", out);
+  run<DMMA, FMUL>("DMMA + FMUL", out);
+  run<DMMA, LDS>("DMMA + LDS.128", out);
+  run<LDS, NONE>("LDS.128", out);
+  run<LDS, WIDE>("LDS.128 + IMAD.WIDE", out);
   printf("%s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;
 }
