@@ -123,13 +123,6 @@ typedef struct {
 int         ptar_version(void);
 const char* ptar_last_error(void);
 
-/* Layout of ptar_gen_params.Ftile the fused generator of this build expects (rc == 16, Cbuf == NULL):
- *   0  Ftile[tile][J][64]                   basis value of column j at epoch e of the tile
- *   1  Ftile[tile][ceil(J/4)][64][4]        k-quad interleaved (element j at [j/4][e][j%4]), rows j >= J zero
- *      -- the operand layout of the fp64 tensor-path epoch GEMM (DMMA.8x8x4 fragments are 32 consecutive doubles).
- * The 512-thread build (rc == 32) and the epoch kernel of the two-kernel schedule (Cbuf != NULL) always take 0. */
-int         ptar_gen_ftile_layout(void);
-
 /* Lower Cholesky factor of `batch` SPD matrices A[b][n][n] (row-major) -> L (strict upper
  * part zeroed).  info[b] = 0, or k>0 if the leading minor of order k is not PD.  n <= 1024. */
 int ptar_cholesky_lower(double* L, const double* A, int n, int batch, int* info, void* stream);

@@ -20,7 +20,7 @@ TOA_ALIGN = 4
 F_WHITE, F_ECORR, F_RED, F_GWB, F_DET, F_WHITE1 = 1, 2, 4, 8, 16, 32
 K_WHITE1, K_WHITE2, K_ECORR, K_RED, K_GWB = 1, 2, 3, 4, 5
 
-EXPORTS = ("ptar_version", "ptar_gen_ftile_layout", "ptar_last_error", "ptar_cholesky_lower", "ptar_fourier_basis", "ptar_cgw_delay", "ptar_cw_catalog", "ptar_burst_delay", "ptar_memory_delay",
+EXPORTS = ("ptar_version", "ptar_last_error", "ptar_cholesky_lower", "ptar_fourier_basis", "ptar_cgw_delay", "ptar_cw_catalog", "ptar_burst_delay", "ptar_memory_delay",
            "ptar_gwb_mix", "ptar_gwb_synth", "ptar_generate", "ptar_generate_stage", "ptar_philox_normals", "ptar_run_job",
            "ptar_run_job_to_host")
 
@@ -72,7 +72,6 @@ def lib():
     L = C.CDLL(LIB_PATH)
     vp, i32, i64, u64 = C.c_void_p, C.c_int, C.c_int64, C.c_uint64
     L.ptar_version.restype = C.c_int
-    L.ptar_gen_ftile_layout.restype = C.c_int
     L.ptar_last_error.restype = C.c_char_p
     L.ptar_cholesky_lower.argtypes = [vp, vp, i32, i32, vp, vp]
     L.ptar_fourier_basis.argtypes = [vp, vp, i64, vp, vp, vp, i32, i32, i64, vp]
@@ -88,7 +87,7 @@ def lib():
     L.ptar_run_job.argtypes = [C.POINTER(Job), i64, C.c_int32, vp, vp]
     L.ptar_run_job_to_host.argtypes = [C.POINTER(Job), i64, i64, C.c_int32, vp, vp, vp, vp, vp]
     for name in EXPORTS:
-        if name not in ("ptar_version", "ptar_gen_ftile_layout", "ptar_last_error"):
+        if name not in ("ptar_version", "ptar_last_error"):
             getattr(L, name).restype = C.c_int
     _lib = L
     return L

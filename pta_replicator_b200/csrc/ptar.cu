@@ -279,7 +279,6 @@ int launch_gen(const ptar_gen_params& p, cudaStream_t st) {
 extern "C" {
 
 int ptar_version(void) { return PTAR_VERSION; }
-int ptar_gen_ftile_layout(void) { return GEN_GEMM_DMMA ? 1 : 0; }
 const char* ptar_last_error(void) { return g_err; }
 
 int ptar_cholesky_lower(double* L, const double* A, int n, int batch, int* info, void* stream) {

@@ -43,29 +43,13 @@ constexpr int EP = PTAR_TILE_EPOCHS;  // 64
 #define GEN_UNROLL 2  // two realization groups in flight per thread: +1.4 % measured (4: same)
 #endif
 constexpr int kGenUnroll = GEN_UNROLL;
-// Epoch GEMM of the RC = 16 build on the fp64 tensor path (mma.sync.m8n8k4.f64, SASS DMMA.8x8x4) instead of DFMA:
-// same FP64-pipe time, but one warp instruction per 256 FMAs frees the dispatch slots the TOA stages of the
-// co-resident CTAs are bound by.  Needs the basis tile in the k-quad interleaved layout
-// Ftile[tile][J4/4][64][4] (ptar_gen_ftile_layout() == 1).
-#ifndef GEN_GEMM_DMMA
-#define GEN_GEMM_DMMA 0
-#endif
-#ifndef PTAR_DMMA
-#define PTAR_DMMA(c0, c1, a, b)                                                                         \
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"          \
-               : "+d"(c0), "+d"(c1)                                                                      \
-               : "d"(a), "d"(b))
-#endif
-__host__ __device__ constexpr bool gen_uses_dmma(int RC) { return GEN_GEMM_DMMA != 0 && RC == 16; }
 
 __host__ __device__ constexpr int gen_css(int RC) { return 3 * RC + 2; }  // even (16-B rows), 4e-word bank skew
 
 __host__ __device__ inline size_t gen_smem_bytes(int J, int RC) {
   // mbarrier (16 B) + max(Fs[J][64] + As[3][J][RC], Cs[64][css])  (Cs aliases the GEMM operands)
-  if (gen_uses_dmma(RC)) J = (J + 3) & ~3;  // k-quads; rows J..J4-1 are zero
   const size_t ops = size_t(J) * EP + size_t(3) * J * RC;
-  size_t cs = size_t(EP) * gen_css(RC);
-  if (gen_uses_dmma(RC)) cs += size_t(3) * 12 * (16 * RC / 4);  // split-K scratch behind Cs
+  const size_t cs = size_t(EP) * gen_css(RC);
   return 16 + sizeof(double) * (ops > cs ? ops : cs);
 }
 
@@ -87,9 +71,7 @@ __device__ __forceinline__ void gen_body(const ptar_gen_params& P, const PhiloxK
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
   double* Fs = reinterpret_cast<double*>(smem_raw + 16);
   const int J = P.J;
-  constexpr bool DM = gen_uses_dmma(RC);
-  const int J4 = DM ? ((J + 3) & ~3) : J;  // DMMA build: k-quads, rows J..J4-1 of both operands are zero
-  double* As = Fs + size_t(J4) * EP;
+  double* As = Fs + size_t(J) * EP;
   double* Cs = Fs;  // written only after the GEMM has consumed Fs / As
   constexpr int CSS = gen_css(RC);
   constexpr int RG = RC / 4;
@@ -162,8 +144,8 @@ __device__ __forceinline__ void gen_body(const ptar_gen_params& P, const PhiloxK
     }
     __syncthreads();
     if (tid == 0) {
-      const uint32_t bytes = static_cast<uint32_t>(sizeof(double) * J4 * EP);
-      const double* src = P.Ftile + size_t(tile_idx) * J4 * EP;
+      const uint32_t bytes = static_cast<uint32_t>(sizeof(double) * J * EP);
+      const double* src = P.Ftile + size_t(tile_idx) * J * EP;
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes)
                    : "memory");
       asm volatile(
@@ -182,16 +164,10 @@ __device__ __forceinline__ void gen_body(const ptar_gen_params& P, const PhiloxK
       double* A0 = As;
       double* A1 = As + size_t(J) * RC;
       double* A2 = As + size_t(2) * J * RC;
-      for (int idx = tid; idx < (J4 / 2) * RG; idx += GEN_THREADS) {
+      for (int idx = tid; idx < (J / 2) * RG; idx += GEN_THREADS) {
         const int k = idx / RG, rg = idx % RG;
         const int je = 2 * k, jo = 2 * k + 1;
         double ye[4], yo[4];
-        if (DM && je >= J) {  // zero rows that pad J to a multiple of 4
-          double2* q = reinterpret_cast<double2*>(As + (size_t(je >> 2) * (3 * RC) + rg * 12) * 4 + (je & 3));
-#pragma unroll
-          for (int c = 0; c < 12; ++c) q[2 * c] = make_double2(0.0, 0.0);
-          continue;
-        }
         if (INJECT) {
 #pragma unroll
           for (int l = 0; l < 4; ++l) {
@@ -212,29 +188,16 @@ __device__ __forceinline__ void gen_body(const ptar_gen_params& P, const PhiloxK
         }
         const double se = scale[je], so = scale[jo], w = om[k];
         const double h = -0.5 * w * w;
-        if (DM) {
-          // B operand of the DMMA GEMM: As[j / 4][n = realization * 3 + order][j % 4]; the (cos, sin) pair of a
-          // frequency is two adjacent k-slots of one row, i.e. one 16-byte store per (realization, order)
-          double2* q = reinterpret_cast<double2*>(As + (size_t(je >> 2) * (3 * RC) + rg * 12) * 4 + (je & 3));
 #pragma unroll
-          for (int l = 0; l < 4; ++l) {
-            const double a_e = se * ye[l], a_o = so * yo[l];
-            q[2 * (3 * l + 0)] = make_double2(a_e, a_o);
-            q[2 * (3 * l + 1)] = make_double2(sgn_even * w * a_o, -sgn_even * w * a_e);
-            q[2 * (3 * l + 2)] = make_double2(h * a_e, h * a_o);
-          }
-        } else {
-#pragma unroll
-          for (int l = 0; l < 4; ++l) {
-            const int c = rg * 4 + l;
-            const double a_e = se * ye[l], a_o = so * yo[l];
-            A0[je * RC + c] = a_e;
-            A0[jo * RC + c] = a_o;
-            A1[je * RC + c] = sgn_even * w * a_o;
-            A1[jo * RC + c] = -sgn_even * w * a_e;
-            A2[je * RC + c] = h * a_e;
-            A2[jo * RC + c] = h * a_o;
-          }
+        for (int l = 0; l < 4; ++l) {
+          const int c = rg * 4 + l;
+          const double a_e = se * ye[l], a_o = so * yo[l];
+          A0[je * RC + c] = a_e;
+          A0[jo * RC + c] = a_o;
+          A1[je * RC + c] = sgn_even * w * a_o;
+          A1[jo * RC + c] = -sgn_even * w * a_e;
+          A2[je * RC + c] = h * a_e;
+          A2[jo * RC + c] = h * a_o;
         }
       }
     }
@@ -251,67 +214,6 @@ __device__ __forceinline__ void gen_body(const ptar_gen_params& P, const PhiloxK
             : "memory");
       }
     }
-    if constexpr (DM) {
-      // C[e][n] = sum_j F[j][e] * A[n][j], n = realization * 3 + order, on DMMA.8x8x4: a warp owns 16 epochs x 24
-      // columns (2 x 3 tiles), 8 / nsplit warps per column-slice group; the fragments are 32 consecutive doubles
-      // of the k-quad interleaved operands (conflict-free 8-byte loads).
-      const int warp = tid >> 5, lane = tid & 31, fg = lane >> 2, fq = lane & 3;
-      const int wpg = (GEN_THREADS / 32) / nsplit;
-      const int ksw = warp / wpg, wg = warp % wpg;
-      const int n_base = (wg & 1) * 24, e_base = (wg >> 1) * 16;
-      double c[2][3][2];
-#pragma unroll
-      for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < 3; ++ni) c[mi][ni][0] = c[mi][ni][1] = 0.0;
-      if (e_base < tile.n_ep) {
-        const int KS = J4 >> 2;
-        const int s_lo = (KS * ksw) / nsplit, s_hi = (KS * (ksw + 1)) / nsplit;
-        const bool second = e_base + 8 < tile.n_ep;
-        const double* fa = Fs + size_t(e_base + fg) * 4 + fq;
-        const double* ba = As + size_t(n_base + fg) * 4 + fq;
-        for (int sq = s_lo; sq < s_hi; ++sq) {
-          const double* f = fa + size_t(sq) * (4 * EP);
-          const double* b = ba + size_t(sq) * (4 * 3 * RC);
-          const double a0 = f[0], b0 = b[0], b1 = b[32], b2 = b[64];
-          PTAR_DMMA(c[0][0][0], c[0][0][1], a0, b0);
-          PTAR_DMMA(c[0][1][0], c[0][1][1], a0, b1);
-          PTAR_DMMA(c[0][2][0], c[0][2][1], a0, b2);
-          if (second) {
-            const double a1 = f[32];
-            PTAR_DMMA(c[1][0][0], c[1][0][1], a1, b0);
-            PTAR_DMMA(c[1][1][0], c[1][1][1], a1, b1);
-            PTAR_DMMA(c[1][2][0], c[1][2][1], a1, b2);
-          }
-        }
-      }
-      __syncthreads();  // everyone is done reading Fs / As: Cs and the scratch behind it may overwrite them
-      if (nsplit > 1) {  // split-K: groups >= 1 park their 12 partial sums in scratch[group - 1][x][thread of group]
-        double* scratch = Fs + size_t(EP) * CSS;
-        const int tgd = tid % gthreads;
-        if (ksw > 0) {
-          double* sp = scratch + size_t(ksw - 1) * 12 * gthreads + tgd;
-#pragma unroll
-          for (int x = 0; x < 12; ++x) sp[x * gthreads] = c[x / 6][(x / 2) % 3][x & 1];
-        }
-        __syncthreads();
-        if (ksw == 0) {
-          for (int g = 1; g < nsplit; ++g) {
-            const double* sp = scratch + size_t(g - 1) * 12 * gthreads + tgd;
-#pragma unroll
-            for (int x = 0; x < 12; ++x) c[x / 6][(x / 2) % 3][x & 1] += sp[x * gthreads];
-          }
-        }
-      }
-      if (ksw == 0) {
-#pragma unroll
-        for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-          for (int ni = 0; ni < 3; ++ni)
-            *reinterpret_cast<double2*>(Cs + size_t(e_base + mi * 8 + fg) * CSS + n_base + ni * 8 + 2 * fq) =
-                make_double2(c[mi][ni][0], c[mi][ni][1]);
-      }
-    } else {
     // C[e][r][d] = sum_j F[j][e] * A[d][j][r]   (this thread: columns [jlo, jhi))
     if (e0 < tile.n_ep) {
       const int jlo = (J * ks) / nsplit, jhi = (J * (ks + 1)) / nsplit;
@@ -354,9 +256,8 @@ __device__ __forceinline__ void gen_body(const ptar_gen_params& P, const PhiloxK
       }
       __syncthreads();
     }
-    }  // !DM
   }
-  if (has_epoch && ks == 0 && !(DM && has_red)) {
+  if (has_epoch && ks == 0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       double* c = Cs + (e0 + i) * CSS + rr * 3;

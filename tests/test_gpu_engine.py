@@ -146,18 +146,6 @@ def test_gwb_throughput_factor_has_the_reference_covariance():
     assert np.allclose(np.triu(L[:, :L.shape[0]], 1), 0.0)
 
 
-def _same_generator(x, y):
-    """Fused generator against another schedule of the same arithmetic (two-kernel schedule, 512-thread CTAs).  With
-    the DFMA epoch GEMM they share one summation order and agree bit for bit; when the fused 256-thread kernel
-    runs its epoch GEMM on the fp64 tensor path (ptar_gen_ftile_layout() == 1) the 60-term sums are associated
-    differently: equal to 1e-13 of the rms (fp64 rounding of the red-noise sum)."""
-    import torch
-    from pta_replicator_b200 import _cabi
-    if _cabi.lib().ptar_gen_ftile_layout() == 0:
-        return torch.equal(x, y)
-    return float((x - y).abs().max()) <= 1e-13 * float(x.std())
-
-
 def test_shards_and_chunks_are_bitwise_reproducible():
     """A realization depends only on (seed, global id): any split over calls / chunks / GPUs is identical."""
     import torch
@@ -175,11 +163,11 @@ def test_shards_and_chunks_are_bitwise_reproducible():
     b.split_epoch = True                      # epoch kernel + TOA kernel: same arithmetic, same bits
     b.default_chunk = 512
     b._job_cache_key = None
-    assert _same_generator(b.generate(40, seed=3, real0=8), full)
+    assert torch.equal(b.generate(40, seed=3, real0=8), full)
     b.split_epoch = False
     b._job_cache_key = None
     wide = b.generate(40, seed=3, real0=8, rc=32)          # 512-thread CTAs, 32 realizations each
-    assert _same_generator(full, wide)
+    assert torch.equal(full, wide)
     h = b.generate_to_host(40, seed=3, real0=8, chunk=16)
     assert torch.equal(full.cpu(), h)
 
@@ -208,7 +196,7 @@ def test_two_kernel_schedule_is_bitwise_the_fused_generator(exact):
     b = _batch(psrs, spec, exact_epochs=exact)
     for n in (1, 5, 16, 17, 33, 48, 70):
         x, y = both(b, n, seed=11, real0=4)
-        assert _same_generator(x, y), n
+        assert torch.equal(x, y), n
     st = b.compile()
     R, P = 19, len(spec)
     rng = np.random.default_rng(6)
@@ -217,7 +205,7 @@ def test_two_kernel_schedule_is_bitwise_the_fused_generator(exact):
                zrn=torch.from_numpy(rng.standard_normal((R, P, 60))),
                gwb_z=torch.from_numpy(rng.standard_normal((R, P, st["gwb_T_Jreal"]))))
     x, y = both(b, R, inject=inj)
-    assert _same_generator(x, y)
+    assert torch.equal(x, y)
     # subsets: ECORR only (no GEMM), red noise only, GWB only
     for which in ("ecorr", "red", "gwb"):
         s = PulsarBatch(psrs, exact_epochs=exact)
@@ -229,7 +217,7 @@ def test_two_kernel_schedule_is_bitwise_the_fused_generator(exact):
         if which == "gwb":
             s.set_gwb(-14.0, 4.0)
         x, y = both(s, 21, seed=2)
-        assert _same_generator(x, y) and float(x.abs().max()) > 0, which
+        assert torch.equal(x, y) and float(x.abs().max()) > 0, which
 
 
 def test_ragged_realization_counts():

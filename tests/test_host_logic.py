@@ -236,65 +236,3 @@ def test_population_partition_matches_the_reference_function():
     d = z_to_dcom(np.array([1e-3, 0.5, 1.0]))
     mpc = 3.0856775814913674e24
     assert abs(d[0] / mpc - 1e-3 * 2.99792458e5 / 69.32) < 2e-3 and d[0] < d[1] < d[2] and 3200 < d[2] / mpc < 3500
-
-
-@pytest.mark.parametrize("n_ep", [7, 16, 17, 32, 33, 64])
-def test_tensor_path_epoch_gemm_operand_layout(n_ep):
-    """The layout contract of ptar_gen_ftile_layout() == 1 (csrc/ptar_generate.cuh, DMMA branch of gen_body): the basis
-    tile in k-quad interleaved order (engine.ftile_kquad), the coefficient rows as As[j/4][realization*3+order][j%4],
-    fragments = 32 consecutive doubles, a warp = 16 epochs x 24 columns, 8 / nsplit warps per split-K group.  Emulated
-    lane by lane in numpy with the PTX m8n8k4 fragment map (a: row = lane/4, col = lane%4; b: row = lane%4,
-    col = lane/4; c: row = lane/4, cols = 2*(lane%4), +1) and compared with the plain contraction."""
-    import torch
-
-    from pta_replicator_b200.engine import ftile_kquad
-    rng = np.random.default_rng(n_ep)
-    J, EP, RC, CSS = 58, 64, 16, 50            # J % 4 == 2: one zero pair pads the last k-quad
-    J4 = (J + 3) & ~3
-    F = rng.standard_normal((J, EP))
-    F[:, n_ep:] = 0.0
-    A = rng.standard_normal((3, J, RC))
-    Fs = ftile_kquad(torch.from_numpy(F.reshape(-1).copy()), 1, J).numpy()
-    As = np.full((J4 // 4) * 3 * RC * 4, np.nan)
-    for idx in range((J4 // 2) * (RC // 4)):   # the coefficient pass: one item = (frequency pair, 4 realizations)
-        k, rg = divmod(idx, RC // 4)
-        je = 2 * k
-        base = ((je >> 2) * (3 * RC) + rg * 12) * 4 + (je & 3)
-        for l in range(4):
-            for d in range(3):
-                pair = (A[d, je, rg * 4 + l], A[d, je + 1, rg * 4 + l]) if je < J else (0.0, 0.0)
-                As[base + 4 * (3 * l + d): base + 4 * (3 * l + d) + 2] = pair
-    assert not np.isnan(As).any()
-    nsplit = 4 if n_ep <= 16 else (2 if n_ep <= 32 else 1)
-    wpg, KS = 8 // nsplit, J4 >> 2
-    lanes = np.arange(32)
-    fg, fq = lanes >> 2, lanes & 3
-    acc = np.zeros((8, 32, 2, 3, 2))
-    for warp in range(8):
-        ksw, wg = divmod(warp, wpg)
-        n_base, e_base = (wg & 1) * 24, (wg >> 1) * 16
-        if e_base >= n_ep:
-            continue
-        for sq in range((KS * ksw) // nsplit, (KS * (ksw + 1)) // nsplit):
-            fa = (e_base + fg) * 4 + fq + sq * 4 * EP
-            ba = (n_base + fg) * 4 + fq + sq * 4 * 3 * RC
-            for mi in range(2 if e_base + 8 < n_ep else 1):
-                a = np.zeros((8, 4))
-                a[fg, fq] = Fs[fa + 32 * mi]
-                for ni in range(3):
-                    b = np.zeros((4, 8))
-                    b[fq, fg] = As[ba + 32 * ni]
-                    D = a @ b
-                    acc[warp, :, mi, ni, 0] += D[fg, 2 * fq]
-                    acc[warp, :, mi, ni, 1] += D[fg, 2 * fq + 1]
-    Cs = np.full(EP * CSS, np.nan)
-    for warp in range(wpg):                    # group 0 adds the other groups' partial sums and writes Cs
-        c = sum(acc[g * wpg + warp] for g in range(nsplit))
-        n_base, e_base = (warp & 1) * 24, (warp >> 1) * 16
-        for mi in range(2):
-            for ni in range(3):
-                o = (e_base + mi * 8 + fg) * CSS + n_base + ni * 8 + 2 * fq
-                Cs[o], Cs[o + 1] = c[:, mi, ni, 0], c[:, mi, ni, 1]
-    got = Cs.reshape(EP, CSS)[:n_ep, :48]
-    ref = np.einsum("je,djr->erd", F, A).reshape(EP, 48)[:n_ep]
-    assert not np.isnan(got).any() and np.abs(got - ref).max() < 1e-13

@@ -6,7 +6,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
-enum Op { WIDE, MHI, MLO, MUFU, CVT, DFMA, LOP, FMUL, NONE, DMMA, LDS };
+enum Op { WIDE, MHI, MLO, MUFU, CVT, DFMA, LOP, FMUL, NONE, DMMA };
 
 template <int OP>
 __device__ __forceinline__ void op(uint32_t& a, uint32_t& b, float& f, double& d) {
@@ -31,17 +31,12 @@ __device__ __forceinline__ void op(uint32_t& a, uint32_t& b, float& f, double& d
   } else if (OP == DMMA) {  // D(8x8) = A(8x4) B(4x8) + C on the FP64 tensor path: 256 FMA per warp instruction
     asm volatile("{.reg .f64 c1; mov.f64 c1, %0; mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, c1}, {%1}, {%2}, {%0, c1};}"
                  : "+d"(d) : "d"(1.0e-3), "d"(1.0e-3));
-  } else if (OP == LDS) {   // 128-bit shared load whose address depends on the previous one
-    asm volatile("{.reg .b32 x, y, z, w; ld.shared.v4.b32 {x, y, z, w}, [%0]; and.b32 %0, x, 0x3ff0;}" : "+r"(a));
   }
 }
 
 template <int A, int B>
 __global__ void __launch_bounds__(256, 4) k(float* out, int iters) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  __shared__ uint4 sm[1024];
-  for (int i = threadIdx.x; i < 1024; i += blockDim.x) sm[i] = make_uint4((i * 16) & 0x3ff0, 0, 0, 0);
-  __syncthreads();
   uint32_t a[4], b[4], a2[4], b2[4];
   float f[4], g[4];
   double d[4], e[4];
@@ -113,9 +108,6 @@ int main() {
   run<DMMA, MUFU>("DMMA + MUFU", out);
   run<DMMA, LOP>("DMMA + IADD3+LOP3", out);
   run<DMMA, FMUL>("DMMA + FMUL", out);
-  run<DMMA, LDS>("DMMA + LDS.128", out);
-  run<LDS, NONE>("LDS.128", out);
-  run<LDS, WIDE>("LDS.128 + IMAD.WIDE", out);
   printf("%s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;
 }
