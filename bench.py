@@ -150,7 +150,7 @@ def main():
         ge.build()               # no-op when the in-tree .so is up to date
     if dist is not None:
         dist.barrier()           # the other ranks load the library only after rank 0 has (re)built it
-    from pta_replicator_b200 import _cabi, synthetic
+    from pta_replicator_b200 import synthetic
     from pta_replicator_b200.engine import PulsarBatch
 
     psrs, noise = synthetic.make_ng15_like(args.kind)

@@ -13,7 +13,6 @@ from __future__ import annotations
 import numpy as np
 
 from . import _cabi
-from .constants import DAY_IN_SEC
 from .engine import PulsarBatch
 from .simulate import SimulatedPulsar, TimeArray
 
