@@ -130,6 +130,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
     ap.add_argument("--split", action="store_true", help="epoch kernel + TOA kernel (two launches) instead of the fused generator")
+    ap.add_argument("--taylor-tol", type=float, default=1e-14,
+                    help="PulsarBatch(rn_taylor_tol=...): remainder bound of the in-epoch Taylor step, relative to the red-noise rms")
     ap.add_argument("--gather", action="store_true", help="also time an NCCL all-gather of one chunk of residuals")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -154,7 +156,7 @@ def main():
     from pta_replicator_b200.engine import PulsarBatch
 
     psrs, noise = synthetic.make_ng15_like(args.kind)
-    b = PulsarBatch(psrs)
+    b = PulsarBatch(psrs, rn_taylor_tol=args.taylor_tol)
     b.white_merged = bool(args.merged_white)
     synthetic.ng15_recipe(b, noise)
     if args.chunk:
@@ -247,6 +249,7 @@ def main():
             "config": {"workload": f"ng15-{args.kind}: 67 psr, sum N_toa={b.n_toa_total}, EFAC/EQUAD+ECORR(1s)+RN(30 comp)+HD GWB(npts=600,howml=10)",
                        "realizations_per_step_per_gpu": R, "rng": "in-kernel Philox4x32-10, fp32 Box-Muller",
                        "white_draws_per_toa": 1 if args.merged_white else 2, "gwb_chunk": chunk_real,
+                       "rn_taylor_tol": args.taylor_tol,
                        "l2": f"output per step {R * b.ld * 8 / 1e9:.2f} GB > L2 (126 MB); no flush needed",
                        "parallelism": f"realization-sharded x{world}, no data-path collective"},
             "kernels": kern, "kernels_timing": "second pass of the same K steps with CUDA events around every launch (same stream, same schedule)",
@@ -255,7 +258,7 @@ def main():
 
     # ---- variant: one merged white draw per TOA (identical distribution; PTAR_F_WHITE1), rank 0, N == 1 only
     if world == 1 and not args.merged_white and not args.no_variants:
-        b1 = PulsarBatch(psrs)
+        b1 = PulsarBatch(psrs, rn_taylor_tol=args.taylor_tol)
         b1.white_merged = True
         b1.split_epoch = bool(args.split)
         synthetic.ng15_recipe(b1, noise)
