@@ -115,9 +115,11 @@ typedef struct {
   int32_t nreal;
   int32_t rc;         /* realizations per CTA: 16 (256 threads) or 32 (512 threads); 0 = default */
   /* optional scratch for the two-kernel schedule (epoch kernel -> TOA kernel): at least
-   * (sum of n_ep over tiles) * ceil(nreal/16) * 50 doubles; NULL selects the fused kernel */
+   * c_rows * ceil(nreal/rc) * (3 rc + 2) doubles (rc = 16: 50 per row); NULL selects the fused kernel.
+   * The library checks cbuf_len against that size before it launches. */
   double* Cbuf;
   int64_t cbuf_len;   /* doubles available at Cbuf */
+  int64_t c_rows;     /* sum of n_ep over all tiles (rows of the epoch blocks)  */
 } ptar_gen_params;
 
 int         ptar_version(void);

@@ -44,7 +44,7 @@ class GenParams(C.Structure):
         ("n_bucket_total", C.c_int64),
         ("seed", C.c_uint64), ("real0", C.c_int64),
         ("out", C.c_void_p), ("ld_out", C.c_int64), ("nreal", C.c_int32), ("rc", C.c_int32),
-        ("Cbuf", C.c_void_p), ("cbuf_len", C.c_int64),
+        ("Cbuf", C.c_void_p), ("cbuf_len", C.c_int64), ("c_rows", C.c_int64),
     ]
 
 

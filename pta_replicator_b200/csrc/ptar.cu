@@ -20,6 +20,26 @@ int fail(int code, const char* fmt, const char* detail = "") {
   return code;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: remember, per kernel and
+// device, that the opt-in has been made (one process may drive several GPUs).
+constexpr int kMaxDevices = 64;
+struct SmemOptIn {
+  bool done[kMaxDevices] = {};
+};
+template <class Kernel>
+int opt_in_smem(Kernel k, SmemOptIn& state, size_t bytes, const char* what) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = -1;
+  if (dev >= 0 && state.done[dev]) return 0;
+  const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+    return -100;
+  }
+  if (dev >= 0) state.done[dev] = true;
+  return 0;
+}
+
 int check_launch(const char* what) {
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -230,13 +250,14 @@ int launch_stage(const ptar_gen_params& p, cudaStream_t st) {
   size_t smem = ptar::gen_smem_bytes(p.J, RC);
   if (STAGE == 2) smem = 16 + sizeof(double) * ptar::EP * ptar::gen_css(RC);
   if (smem > 227 * 1024) return fail(-3, "ptar_generate: J too large for shared memory%s");
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
-    cudaFuncSetAttribute(ptar::gen_kernel<RC, INJECT, WHITE, DET, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    attr_set = true;
-  }
+  static SmemOptIn optin;  // per instantiation
+  if (int rc = opt_in_smem(ptar::gen_kernel<RC, INJECT, WHITE, DET, STAGE>, optin, 227 * 1024, "ptar_generate")) return rc;
   const dim3 grid((p.nreal + RC - 1) / RC, p.n_tiles);
   if (grid.y > 65535) return fail(-3, "ptar_generate: more than 65535 tiles%s");
+  if (STAGE != 0 && p.Cbuf) {  // the Cs blocks of this build must fit the scratch the caller gave
+    const int64_t need = p.c_rows * int64_t(grid.x) * ptar::gen_css(RC);
+    if (p.c_rows <= 0 || p.cbuf_len < need) return fail(-2, "ptar_generate: Cbuf too small for this rc (need c_rows * ceil(nreal/rc) * (3 rc + 2) doubles)%s");
+  }
   ptar::gen_kernel<RC, INJECT, WHITE, DET, STAGE><<<grid, ptar::gen_threads(RC), smem, st>>>(p, ptar::philox_keys(p.seed));
   return check_launch("ptar_generate");
 }
@@ -246,13 +267,14 @@ template <bool INJECT>
 int launch_epoch(const ptar_gen_params& p, cudaStream_t st) {
   const size_t smem = ptar::epoch_smem_bytes(p.J);
   if (smem > 227 * 1024) return fail(-3, "ptar_generate: J too large for shared memory%s");
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(ptar::epoch_kernel<INJECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    attr_set = true;
-  }
+  static SmemOptIn optin;
+  if (int rc = opt_in_smem(ptar::epoch_kernel<INJECT>, optin, 227 * 1024, "ptar_generate (epoch kernel)")) return rc;
   const dim3 grid((p.nreal + ptar::EPK_RB - 1) / ptar::EPK_RB, p.n_tiles);
   if (grid.y > 65535) return fail(-3, "ptar_generate: more than 65535 tiles%s");
+  {
+    const int64_t need = p.c_rows * int64_t((p.nreal + 15) / 16) * ptar::EPK_CSS;
+    if (p.c_rows <= 0 || p.cbuf_len < need) return fail(-2, "ptar_generate: Cbuf too small (need c_rows * ceil(nreal/16) * 50 doubles)%s");
+  }
   ptar::epoch_kernel<INJECT><<<grid, ptar::EPK_THREADS, smem, st>>>(p, ptar::philox_keys(p.seed));
   return check_launch("ptar_generate (epoch kernel)");
 }
@@ -334,11 +356,14 @@ int ptar_cw_catalog(double* out, const double* t, int64_t n_toa, const double* p
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cw_prefactor_kernel<<<static_cast<unsigned>((n_src + 255) / 256), 256, 0, st>>>(pre, cat, n_src, phat_host[0], phat_host[1],
                                                                                    phat_host[2], pdist_kpc, pphase, use_pphase);
+  if (int rc = check_launch("ptar_cw_catalog (prefactors)")) return rc;
   const int64_t per = (n_src + n_slices - 1) / n_slices;
   const dim3 grid(static_cast<unsigned>((n_toa + CW_TOAS - 1) / CW_TOAS), static_cast<unsigned>(n_slices));
+  if (grid.y > 65535) return fail(-3, "ptar_cw_catalog: more than 65535 slices%s");
   cw_catalog_kernel<<<grid, CW_TOAS, 0, st>>>(partial, t, n_toa, pre, n_src, per, mode, psr_term);
+  if (int rc = check_launch("ptar_cw_catalog (sources x TOAs)")) return rc;
   cw_reduce_kernel<<<static_cast<unsigned>((n_toa + 255) / 256), 256, 0, st>>>(out, partial, n_toa, n_slices, accumulate);
-  return check_launch("ptar_cw_catalog");
+  return check_launch("ptar_cw_catalog (slice reduction)");
 }
 
 int ptar_gwb_mix(double* Zm, const double* M, const double* zin, int n_psr, int J, int64_t nreal, uint64_t seed,
@@ -352,10 +377,12 @@ int ptar_gwb_mix(double* Zm, const double* M, const double* zin, int n_psr, int 
   const size_t smem = sizeof(double) * (size_t(KP) * ptar::MX_ZS + size_t(NP) * (KP + 4));
   if (smem > 227 * 1024) return fail(-3, "ptar_gwb_mix: too many pulsars for shared memory%s");
   if (zin) {
-    cudaFuncSetAttribute(ptar::gwb_mix_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    static SmemOptIn optin;
+    if (int rc = opt_in_smem(ptar::gwb_mix_dmma_kernel<true>, optin, 227 * 1024, "ptar_gwb_mix")) return rc;
     ptar::gwb_mix_dmma_kernel<true><<<grid, 256, smem, st>>>(Zm, M, zin, n_psr, J, nreal, ptar::philox_keys(seed), real0);
   } else {
-    cudaFuncSetAttribute(ptar::gwb_mix_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    static SmemOptIn optin;
+    if (int rc = opt_in_smem(ptar::gwb_mix_dmma_kernel<false>, optin, 227 * 1024, "ptar_gwb_mix")) return rc;
     ptar::gwb_mix_dmma_kernel<false><<<grid, 256, smem, st>>>(Zm, M, zin, n_psr, J, nreal, ptar::philox_keys(seed), real0);
   }
   return check_launch("ptar_gwb_mix");
@@ -368,11 +395,8 @@ int ptar_gwb_synth(double* G, int64_t g_ld, const double* A, int64_t lda, const 
   if ((J & 3) || (lda & 1) || lda < J || (g_ld & 1)) return fail(-2, "ptar_gwb_synth: need J %% 4 == 0, even lda >= J, even g_ld%s");
   const int64_t r_blocks = (nreal + ptar::DM_BC - 1) / ptar::DM_BC;
   if (r_blocks > 65535) return fail(-3, "ptar_gwb_synth: too many realizations per call%s");
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(ptar::gwb_synth_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ptar::DM_SMEM));
-    attr_set = true;
-  }
+  static SmemOptIn optin;
+  if (int rc = opt_in_smem(ptar::gwb_synth_dmma_kernel, optin, ptar::DM_SMEM, "ptar_gwb_synth")) return rc;
   const dim3 grid(static_cast<unsigned>(n_tiles), static_cast<unsigned>(r_blocks));
   ptar::gwb_synth_dmma_kernel<<<grid, 256, ptar::DM_SMEM, static_cast<cudaStream_t>(stream)>>>(
       G, g_ld, A, lda, Zm, J, nreal, tile_list, knots, lower_tri);
@@ -472,19 +496,24 @@ int ptar_run_job_to_host(const ptar_job* job, int64_t real0, int64_t nreal, int3
   if (!job || !out_host || !dev_buf0 || !dev_buf1 || chunk <= 0 || (chunk & 3) || nreal <= 0)
     return fail(-1, "ptar_run_job_to_host: bad argument (chunk must be a positive multiple of 4)%s");
   cudaStream_t s0 = static_cast<cudaStream_t>(stream0), s1 = static_cast<cudaStream_t>(stream1);
-  cudaEvent_t gen_done[2], copy_done[2];
+  cudaEvent_t gen_done[2] = {nullptr, nullptr}, copy_done[2] = {nullptr, nullptr};
+  int rc = 0;
+  cudaError_t e = cudaSuccess;
+  auto ok = [&](cudaError_t r) {  // first runtime error wins; later calls are skipped
+    if (e == cudaSuccess && r != cudaSuccess) e = r;
+    return e == cudaSuccess;
+  };
   for (int i = 0; i < 2; ++i) {
-    cudaEventCreateWithFlags(&gen_done[i], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&copy_done[i], cudaEventDisableTiming);
+    ok(cudaEventCreateWithFlags(&gen_done[i], cudaEventDisableTiming));
+    ok(cudaEventCreateWithFlags(&copy_done[i], cudaEventDisableTiming));
   }
   double* bufs[2] = {dev_buf0, dev_buf1};
   const int64_t ld = job->gen.ld_out;
-  int rc = 0;
   int64_t done = 0;
-  for (int c = 0; done < nreal; ++c) {
+  for (int c = 0; done < nreal && e == cudaSuccess; ++c) {
     const int b = c & 1;
     const int32_t n = static_cast<int32_t>(nreal - done < chunk ? nreal - done : chunk);
-    if (c >= 2) cudaStreamWaitEvent(s0, copy_done[b], 0);  // buffer free again
+    if (c >= 2 && !ok(cudaStreamWaitEvent(s0, copy_done[b], 0))) break;  // buffer free again
     ptar_job j = *job;
     if (j.gen.z1) j.gen.z1 += done * ld;
     if (j.gen.z2) j.gen.z2 += done * ld;
@@ -493,20 +522,21 @@ int ptar_run_job_to_host(const ptar_job* job, int64_t real0, int64_t nreal, int3
     if (j.gwb_zin) j.gwb_zin += done * int64_t(j.gen.n_psr) * j.Jg;
     rc = ptar_run_job(&j, real0 + done, n, bufs[b], s0);
     if (rc) break;
-    cudaEventRecord(gen_done[b], s0);
-    cudaStreamWaitEvent(s1, gen_done[b], 0);
-    cudaMemcpyAsync(out_host + done * ld, bufs[b], sizeof(double) * size_t(n) * ld, cudaMemcpyDeviceToHost, s1);
-    cudaEventRecord(copy_done[b], s1);
+    if (!ok(cudaEventRecord(gen_done[b], s0)) || !ok(cudaStreamWaitEvent(s1, gen_done[b], 0))) break;
+    if (!ok(cudaMemcpyAsync(out_host + done * ld, bufs[b], sizeof(double) * size_t(n) * ld, cudaMemcpyDeviceToHost, s1))) break;
+    if (!ok(cudaEventRecord(copy_done[b], s1))) break;
     done += n;
   }
-  cudaStreamSynchronize(s1);
-  cudaStreamSynchronize(s0);
+  // drain both streams even after an error so no copy is still writing out_host when we return
+  const cudaError_t d1 = cudaStreamSynchronize(s1), d0 = cudaStreamSynchronize(s0);
+  ok(d1);
+  ok(d0);
   for (int i = 0; i < 2; ++i) {
-    cudaEventDestroy(gen_done[i]);
-    cudaEventDestroy(copy_done[i]);
+    if (gen_done[i]) cudaEventDestroy(gen_done[i]);
+    if (copy_done[i]) cudaEventDestroy(copy_done[i]);
   }
   if (rc) return rc;
-  const cudaError_t e = cudaGetLastError();
+  ok(cudaGetLastError());
   if (e != cudaSuccess) return fail(-100, "ptar_run_job_to_host: %s", cudaGetErrorString(e));
   return 0;
 }

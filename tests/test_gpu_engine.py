@@ -98,12 +98,16 @@ def test_injected_draws_all_signals_epoch_mode(exact):
     assert worst < TRIG, worst
 
 
-def test_throughput_mode_matches_oracle_fed_with_the_same_philox_stream():
+@pytest.mark.parametrize("merged", [False, True])
+def test_throughput_mode_matches_oracle_fed_with_the_same_philox_stream(merged):
     """Philox mode end to end: the numpy restatement of the stream (oracle/philox.py) is pushed through
-    the numpy oracle; the GWB uses the engine's own factor L (L L^T = T T^T is checked below)."""
+    the numpy oracle; the GWB uses the engine's own factor L (L L^T = T T^T is checked below).
+    merged=True is the default throughput mode (one draw of variance w1^2 + w2^2 per TOA: the oracle's white term
+    gets sqrt(efac^2 sigma^2 + (efac equad)^2) z1); merged=False draws z1 and z2 like the reference."""
     _, spec = load_flags_case()
     psrs = _psrs(spec)
     b = _batch(psrs, spec)
+    b.white_merged = merged
     st = b.compile()
     R, P, seed, real0 = 8, len(spec), 987654321, 40
     out = b.generate(R, seed=seed, real0=real0).cpu().numpy()
@@ -120,7 +124,12 @@ def test_throughput_mode_matches_oracle_fed_with_the_same_philox_stream():
         for i in range(P):
             n, off = b.ntoa[i], b.toa_off[i]
             z1[r, off:off + n] = PH.normals(PH.K_WHITE1, i, rid, n, seed)
-            z2[r, off:off + n] = PH.normals(PH.K_WHITE2, i, rid, n, seed)
+            if merged:      # w1 z1 + w2 z2 with z2 := z1 * 0 and w1 := sqrt(w1^2 + w2^2): fold the ratio into z1
+                pl = b.plan()
+                w1p, w2p = pl["w1"][off:off + n], pl["w2"][off:off + n]
+                z1[r, off:off + n] *= np.sqrt(w1p ** 2 + w2p ** 2) / w1p
+            else:
+                z2[r, off:off + n] = PH.normals(PH.K_WHITE2, i, rid, n, seed)
             nb = (boff[i + 1] if i + 1 < P else st["n_bucket_total"]) - boff[i]
             zb[r, boff[i]:boff[i] + nb] = PH.normals(PH.K_ECORR, i, rid, nb, seed)
             zrn[r, i] = PH.normals(PH.K_RED, i, rid, 60, seed)
@@ -220,6 +229,65 @@ def test_two_kernel_schedule_is_bitwise_the_fused_generator(exact):
         assert torch.equal(x, y) and float(x.abs().max()) > 0, which
 
 
+def test_two_kernel_schedule_with_32_realization_blocks_and_scratch_checks():
+    """rc = 32 in the two-kernel schedule writes 98-double rows (gen_css(32)), not 50: the engine sizes Cbuf from the
+    effective rc, the library refuses a scratch that is too small, and the result equals the fused kernel's bit for bit
+    on realization counts that leave ragged 32-blocks (out-of-bounds Cbuf at n = 40, 16, 48, 80)."""
+    import ctypes as C
+    import torch
+    from pta_replicator_b200 import _cabi
+    _, spec = load_flags_case()
+    b = _batch(_psrs(spec), spec)
+    for n in (16, 40, 48, 80, 33):
+        ref = b.generate(n, seed=9, real0=4)
+        b.split_epoch = True
+        got = b.generate(n, seed=9, real0=4, rc=32)
+        b.split_epoch = False
+        assert torch.equal(ref, got), n
+    # a scratch sized for rc = 16 is rejected for rc = 32 instead of being overrun
+    b.split_epoch = True
+    st = b.compile()
+    job, keep = b._job(st, 40, 9, None, 32)
+    g = job.gen
+    g.cbuf_len = int(st["tiles_host"][:, 4].sum()) * 3 * 50
+    g.real0, g.nreal = 4, 40
+    out = torch.empty((40, b.ld), dtype=torch.float64, device=b.device)
+    g.out = out.data_ptr()
+    if st["flags"] & _cabi.F_GWB:
+        g.G = job.Gbuf
+    rc = _cabi.lib().ptar_generate(C.byref(g), _cabi.current_stream())
+    assert rc == -2 and b"Cbuf too small" in _cabi.lib().ptar_last_error()
+    b.split_epoch = False
+
+
+def test_parity_mode_requires_draws_for_every_enabled_term():
+    """inject= with a term missing must raise instead of silently drawing that term from Philox."""
+    import torch
+    _, spec = load_flags_case()
+    b = _batch(_psrs(spec), spec)
+    st = b.compile()
+    R, P = 2, len(spec)
+    zg = torch.zeros((R, P, st["gwb_T_Jreal"]), dtype=torch.float64)
+    with pytest.raises(ValueError, match="missing: z1, z2, zb, zrn"):
+        b.generate(R, inject=dict(gwb_z=zg))
+
+
+def test_gwb_factor_with_fewer_frequencies_than_grid_points():
+    """howml = 1 gives 2 (Nf - 2) < npts: the throughput factor L is lower trapezoidal with that many columns
+    (shape error) and still has the reference covariance T T^T."""
+    from pta_replicator_b200.engine import PulsarBatch
+    _, spec = load_flags_case()
+    b = PulsarBatch(_psrs(spec))
+    b.set_gwb(-14.0, 13.0 / 3.0, howml=1)
+    st = b.compile()
+    assert st["gwb_T_Jreal"] < st["npts"]
+    L, T = st["gwb_L"].cpu().numpy(), st["gwb_T"].cpu().numpy()
+    A, B = L @ L.T, T @ T.T
+    assert np.linalg.norm(A - B) / np.linalg.norm(B) < 1e-12
+    x = b.generate(8, seed=3)
+    assert bool(np.isfinite(x.cpu().numpy()).all()) and float(x.abs().max()) > 0
+
+
 def test_ragged_realization_counts():
     """nreal not a multiple of the Philox group (4), the CTA chunk (16) or the GWB chunk: a prefix of a
     longer run, bit for bit; single-pulsar / single-signal batches; a chunk that is not a multiple of 16."""
@@ -267,7 +335,7 @@ def test_distribution_white_ecorr_and_merged_draw():
             b.set_ecorr(i, s["l10_ecorr"], flagid="f", flags=be, coarsegrain=1.0 / 86400.0)
         x = b.generate(R, seed=11 + merged)
         pl = b.plan()
-        var_expect = pl["w1"] ** 2 + (0 if merged else pl["w2"] ** 2) + pl["ep_ecorr"][epoch_of_toa(b, pl)] ** 2
+        var_expect = pl["w1"] ** 2 + pl["w2"] ** 2 + pl["ep_ecorr"][epoch_of_toa(b, pl)] ** 2
         real = pl["w1"] > 0
         v = x.var(dim=0, unbiased=True).cpu().numpy()
         ratio = v[real] / var_expect[real]
