@@ -3,19 +3,28 @@
 + HD-correlated GWB residuals (BASELINE.json metric), on N GPUs of one node.
 
     python bench.py --gpus N --steps K --warmup W            # our arm (torchrun for N > 1)
-    python bench.py --impl reference --gpus N --steps K ...   # CPU arm: the oracle port on host cores
+    python bench.py --impl reference --gpus N --steps K ...   # CPU arm: the UNMODIFIED reference on host cores
+    python bench.py --config 3|4|5|exact ...                  # the other BASELINE configs as the headline workload
 
 A step = one batch of R realizations (default 1000) of the whole 67-pulsar array through
-``PulsarBatch.generate`` (Philox mode; outputs stay in HBM).  ``value`` = realizations of all ranks /
-max-over-ranks device time.  ``e2e`` = the same metric through ``ptar_run_job_to_host``: per-step noise
-parameters are copied host->device from pinned memory and every residual is copied back to pinned host
-memory inside the timed region.  ``roofline`` is for the dominant kernel (the fused generator):
-algorithmic bytes = 8 B x sum(N_toa) x realizations per launch, duration from CUDA events
-around every launch in the timed region, peak = MEASURED_PEAKS.json ``hbm_gbs``.
+``PulsarBatch.generate`` (throughput mode: in-kernel Philox; outputs stay in HBM).  ``value`` = realizations of
+all ranks / max-over-ranks device time.  ``e2e`` = the same metric through ``ptar_run_job_to_host``: per-step
+noise parameters are copied host->device from pinned memory and every residual is copied back to pinned host
+memory inside the timed region.  ``roofline`` is for the dominant kernel (the fused generator): algorithmic
+bytes = 8 B x sum(N_toa) x realizations per launch, duration from CUDA events around every
+launch in the timed region, peak = MEASURED_PEAKS.json ``hbm_gbs``.
+
+The default run (what the driver records) also carries, at N = 1: ``other_configs`` (BASELINE configs 3 and 4
+and the literal F @ a generator, ``exact_epochs``), ``variants`` (two white draws per TOA like the reference;
+library-accurate and float64 Box-Muller builds), ``cpu_baseline`` (the unmodified reference and the numpy port
+on the host cores) and ``setup_s``; at N > 1: ``config5`` (BASELINE config 5: 100k realizations of ng15-epoch
+strong-scaled over the ranks with the final NCCL all-gather chunked and overlapped with generation, timed with
+and without the collective).
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -28,6 +37,10 @@ sys.path.insert(0, ROOT)
 
 METRIC = "realizations/sec (67-psr ng15 GWB+RN+ECORR)"
 FALLBACK_HBM_GBS = 6650.0
+SEED = 20250922
+NVLINK_PEER_GBS = 770.0      # B200_PROFILING.md: measured peer copy per direction per GPU (900 nominal)
+CGW3 = dict(gwtheta=1.5707963267948966, gwphi=2.5, mc=1e9, dist=5.0, fgw=1e-8, phase0=0.5, psi=1.5, inc=0.7853981633974483,
+            pdist=1.0, psrTerm=True, evolve=True, tref=53000 * 86400)   # the reference test's source (tests/...:48-53)
 
 
 def peaks():
@@ -37,6 +50,17 @@ def peaks():
             d = json.load(fh)
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def source_hash():
+    """sha256 over the kernel sources: stamps profile captures so a stale `traffic` figure is visible."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "pta_replicator_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            with open(os.path.join(d, f), "rb") as fh:
+                h.update(fh.read())
+    return h.hexdigest()[:16]
 
 
 class ClockSampler(threading.Thread):
@@ -77,41 +101,264 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.samples)}
 
 
-def cpu_arm(ds, n_real, cores, budget_s=None):
-    """realizations/s of the oracle port on `cores` processes; returns (rate, wall, completed)."""
-    from oracle import recipe
-    done, wall = recipe.timed_realizations(ds, n_real, cores, budget_s)
-    return done / wall, wall, done
+# ------------------------------------------------------------------------------------------------ CPU arms
+def cpu_arms(psrs, noise, seconds, want_port=True):
+    """The reference's own CPU path on this box's host cores (bounded samples):
+    kind "reference" = the unmodified functions under the stub harness (oracle/refrecipe.py; staged bytecode from
+    oracle/_ref when /root/reference is absent), kind "port" = the numpy restatement (oracle/recipe.py)."""
+    from oracle import recipe, refrecipe, refstubs
+    from pta_replicator_b200.distributed import usable_cores
+    cores = usable_cores()
+    res = {"cores": cores, "cores_how": "len(sched_getaffinity) capped by the cgroup cpu quota", "os_cpu_count": os.cpu_count()}
+    if refstubs.available():
+        ds = refrecipe.dataset_from_pulsars(psrs, noise)
+        _, one = refrecipe.timed_realizations(ds, 1, 1)
+        done, wall = refrecipe.timed_realizations(ds, cores * 8, cores, budget_s=seconds)
+        res["reference"] = {"value": done / wall, "single_core": 1.0 / one, "realizations": done, "wall_s": wall,
+                            "root": "staged bytecode (oracle/_ref)" if refstubs.available() != refstubs.REFERENCE_ROOT else "/root/reference"}
+    if want_port:
+        ds = recipe.dataset_from_pulsars(psrs, noise)
+        _, one = recipe.timed_realizations(ds, 1, 1)
+        done, wall = recipe.timed_realizations(ds, cores * 8, cores, budget_s=min(seconds, 10.0))
+        res["port"] = {"value": done / wall, "single_core": 1.0 / one, "realizations": done, "wall_s": wall}
+    return res
+
+
+def cpu_baseline_block(arms):
+    kind = "reference" if "reference" in arms else "port"
+    a = arms[kind]
+    what = ("the UNMODIFIED reference functions add_measurement_noise / add_jitter / add_red_noise / add_gwb under the "
+            "stub harness (PINT's adjust_TOAs / Residuals are no-ops: flatters the reference)") if kind == "reference" else \
+           "numpy oracle port (no PINT, no dense U: faster than the unmodified reference)"
+    blk = {"value": a["value"], "unit": "realizations/s", "cores": arms["cores"], "kind": kind,
+           "single_core_value": a["single_core"],
+           "sample": f"{a['realizations']} realizations of the same workload in {a['wall_s']:.1f} s, one single-threaded process per "
+                     f"usable core ({arms['cores']}; os.cpu_count() = {arms['os_cpu_count']}); {what}"}
+    if kind == "reference" and "port" in arms:
+        blk["port"] = {"value": arms["port"]["value"], "single_core_value": arms["port"]["single_core"],
+                       "note": "numpy restatement of the same recipe (oracle/recipe.py), same pool"}
+    return blk
 
 
 def run_reference(args):
-    """The reference arm: the oracle port (the reference is Python + PINT and cannot travel to the box;
-    oracle/recipe.py) on all host cores; each step = one realization per core."""
+    """The reference arm: the reference's own CPU implementation of the path on all usable host cores;
+    a step = one realization per core (pool start-up and one warm-up realization per worker untimed)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import recipe
+    from oracle import recipe, refrecipe, refstubs
     from pta_replicator_b200 import synthetic
+    from pta_replicator_b200.distributed import usable_cores
     psrs, noise = synthetic.make_ng15_like(args.kind)
-    ds = recipe.dataset_from_pulsars(psrs, noise)
-    cores = min(os.cpu_count() or 1, 64)
+    cores = usable_cores()
+    use_ref = bool(refstubs.available())
+    mod = refrecipe if use_ref else recipe
+    ds = mod.dataset_from_pulsars(psrs, noise)
+    _, one = mod.timed_realizations(ds, 1, 1)
     per_step = cores
+    budget = max(20.0, 150.0 / max(args.steps, 1))
     done_total, wall = 0, 0.0
-    for _ in range(args.steps):   # a step = one realization per core; pool start-up and one warm-up pass are untimed
-        _, w, done = cpu_arm(ds, per_step, cores, budget_s=max(20.0, 180.0 / max(args.steps, 1)))
+    for _ in range(args.steps):
+        done, w = mod.timed_realizations(ds, per_step, cores, budget_s=budget)
         done_total += done
         wall += w
     value = done_total / wall
     ntoa = sum(p.toas.ntoas for p in psrs)
+    kind = "reference" if use_ref else "port"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "realizations/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"ng15-{args.kind} 67 psr, sum N_toa={ntoa}, EFAC/EQUAD+ECORR(1s)+RN(30)+HD GWB", "realizations_per_step": per_step},
-            "cpu_baseline": {"value": value, "unit": "realizations/s", "cores": cores, "kind": "port",
-                             "sample": f"{per_step} realizations/step x {args.steps} steps, one process per core, numpy oracle port "
-                                       "(no PINT, no dense U: faster than the unmodified reference)"},
+            "config": {"workload": f"ng15-{args.kind}: 67 psr, sum N_toa={ntoa}, EFAC/EQUAD+ECORR(1s)+RN(30 comp)+HD GWB(npts=600,howml=10)",
+                       "realizations_per_step": per_step},
+            "cpu_baseline": {"value": value, "unit": "realizations/s", "cores": cores, "kind": kind,
+                             "single_core_value": 1.0 / one,
+                             "sample": f"{per_step} realizations/step x {args.steps} steps ({done_total} completed), one single-threaded process "
+                                       f"per usable core ({cores}; os.cpu_count() = {os.cpu_count()}); "
+                                       + ("UNMODIFIED reference functions under the stub harness, "
+                                          + ("staged bytecode oracle/_ref" if refstubs.available() != refstubs.REFERENCE_ROOT else "/root/reference")
+                                          + " (PINT stubs: flatters the reference)" if use_ref else "numpy oracle port")},
             "e2e": {"value": value, "unit": "realizations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def aniso_clm(psrs, lmax=6, seed=SEED):
+    """BASELINE config 4: clm[0] = sqrt(4 pi), clm[1:] ~ 0.05 N(0,1), redrawn until the ORF is PD."""
+    import numpy as np
+    from pta_replicator_b200 import orf as orf_mod
+    radec = orf_mod.psrlocs_from_pulsars(psrs)
+    locs = np.stack([radec[:, 0], np.pi / 2.0 - radec[:, 1]], axis=1)
+    basis = orf_mod.correlated_basis(locs, lmax)
+    rng = np.random.default_rng(seed)
+    for _ in range(100):
+        clm = np.r_[np.sqrt(4 * np.pi), 0.05 * rng.standard_normal((lmax + 1) ** 2 - 1)]
+        orf = 2.0 * sum(c * b for c, b in zip(clm, basis))
+        if np.all(np.linalg.eigvalsh(orf) > 0):
+            return list(clm)
+    raise RuntimeError("no positive-definite anisotropic ORF in 100 draws")
+
+
+def make_batch(cfg, args, merged=True, exact=False, psrs_noise=None):
+    """cfg '2': EFAC/EQUAD + ECORR + RN + HD GWB (the metric config); '3': + CGW; '4': anisotropic GWB lmax = 6;
+    '5': config 2's recipe on ng15-epoch (one TOA per epoch)."""
+    from pta_replicator_b200 import synthetic
+    from pta_replicator_b200.engine import PulsarBatch
+    t0 = time.perf_counter()
+    kind = "epoch" if cfg == "5" else args.kind
+    psrs, noise = psrs_noise if psrs_noise is not None else synthetic.make_ng15_like(kind)
+    b = PulsarBatch(psrs, rn_taylor_tol=args.taylor_tol, exact_epochs=exact)
+    b.white_merged = merged
+    synthetic.ng15_recipe(b, noise, gwb=(cfg != "4"))
+    if cfg == "3":
+        b.add_cgw(**CGW3)
+    if cfg == "4":
+        b.set_gwb(-14.6733, 13.0 / 3.0, lmax=6, clm=aniso_clm(psrs))
+    if args.chunk:
+        b.default_chunk = args.chunk
+    b.split_epoch = bool(args.split)
+    b.compile()
+    return b, psrs, noise, time.perf_counter() - t0, kind
+
+
+def workload_name(cfg, kind, b, exact=False):
+    extra = {"2": "", "3": " + CGW", "4": " (anisotropic ORF, lmax=6)", "5": ""}[cfg]
+    gw = "GWB(npts=600,howml=10)" if cfg == "4" else "HD GWB(npts=600,howml=10)"
+    return (f"ng15-{kind}: 67 psr, sum N_toa={b.n_toa_total}, EFAC/EQUAD+ECORR(1s)+RN(30 comp)+{gw}{extra}"
+            + (", exact_epochs (one epoch per TOA: the literal F @ a)" if exact else ""))
+
+
+def timed_steps(b, R, steps, warmup, rc, world=1, rank=0, dist=None, k0=0):
+    """W untimed + K timed steps bracketed by barrier + synchronize; returns (ms max over ranks, per-kernel dict)."""
+    import numpy as np
+    import torch
+    out = getattr(b, "_bench_out", None)
+    if out is None or out.shape[0] != R:
+        out = torch.zeros((R, b.ld), dtype=torch.float64, device=b.device)
+        b._bench_out = out
+
+    def step(k, timers=None):
+        real0 = (((k0 + k) * world + rank) * R + 3) // 4 * 4     # rank-major blocks of global ids
+        b.generate(R, seed=SEED, real0=real0, out=out, rc=rc, timers=timers)
+
+    for k in range(warmup):
+        step(k)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for k in range(steps):
+        step(warmup + k)
+    e1.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    timers = {}
+    for k in range(steps):     # same K steps again with CUDA events around every launch (same stream, same schedule)
+        step(warmup + steps + k, timers)
+    torch.cuda.synchronize()
+    tms = torch.tensor([ms], dtype=torch.float64, device=b.device)
+    if dist is not None:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    per = {}
+    for name, a, z in timers["events"]:
+        per.setdefault(name, []).append(a.elapsed_time(z))
+    kern = {k: {"launches": len(v), "avg_ms": float(np.mean(v)), "total_ms": float(np.sum(v))} for k, v in per.items()}
+    return float(tms.item()), kern, step
+
+
+def roofline_of(b, kern, R, steps, hbm, how):
+    gen = kern["generate"]
+    n_gen = gen["launches"]
+    alg = 8.0 * b.n_toa_total * (R * steps / n_gen)
+    achieved = alg / (gen["avg_ms"] * 1e-3) / 1e9
+    total = sum(k["total_ms"] for k in kern.values())
+    return {"bound": "hbm", "kernel": "gen_kernel (fused white+ECORR+red+GWB-interp generator)", "achieved": achieved,
+            "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None, "peak_source": how,
+            "algorithmic_bytes_per_launch": alg, "avg_launch_ms": gen["avg_ms"], "share_of_step": gen["total_ms"] / total,
+            "whole_step_frac": 8.0 * b.n_toa_total * R * steps / (total * 1e-3) / 1e9 / hbm}
+
+
+def short_line(b, R, rc, hbm, how, steps=3, warmup=2):
+    ms, kern, _ = timed_steps(b, R, steps, warmup, rc)
+    rf = roofline_of(b, kern, R, steps, hbm, how)
+    return {"value": R * steps / (ms * 1e-3), "unit": "realizations/s", "ms_per_step": ms / steps, "realizations_per_step": R,
+            "kernels_ms_per_step": {k: v["total_ms"] / steps for k, v in kern.items()},
+            "roofline_frac": rf["frac"], "whole_step_frac": rf["whole_step_frac"], "algorithmic_GBps": rf["achieved"]}
+
+
+def config5_block(args, world, rank, dist, hbm):
+    """BASELINE config 5: 100k realizations of ng15-epoch strong-scaled over the ranks, final all-gather chunked
+    (C realizations per rank per chunk) and overlapped with generation on a second stream; timed with and without
+    the collective on the identical schedule; one gathered chunk is checked bit for bit against local regeneration."""
+    import torch
+    from pta_replicator_b200 import distributed as D
+    b, psrs, noise, setup_s, kind = make_batch("5", args)
+    nreal, chunk = args.c5_nreal, args.c5_chunk
+    C, n_chunks, padded = D.gather_plan(nreal, world, chunk)
+    full = torch.empty((padded, b.ld), dtype=torch.float64, device=b.device)
+    comm = torch.cuda.Stream(b.device) if world > 1 else None
+
+    def run(gather):
+        D.generate_gathered(b, nreal, seed=SEED, chunk=chunk, out=full, gather=gather, comm_stream=comm)
+
+    res = {}
+    for gather in (False, True):
+        run(gather)                                   # warm-up (also creates the NCCL channels)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        run(gather)
+        e1.record()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=b.device)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res[gather] = float(t.item())
+    ok = 1
+    if world > 1:   # rows another rank generated, as received here, against regenerating them on this GPU
+        other, c = (rank + 1) % world, n_chunks // 2
+        r0 = D.chunk_ids(c, other, world, C)
+        mine = b.generate(C, seed=SEED, real0=r0)
+        ok = int(torch.equal(mine, full[r0:r0 + C]))
+        t = torch.tensor([ok], dtype=torch.int32, device=b.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        ok = int(t.item())
+    recv = (world - 1) * padded / world * b.ld * 8.0           # bytes every GPU receives
+    blk = {"workload": workload_name("5", kind, b) + f"; {nreal} realizations strong-scaled over {world} GPU(s), chunk-interleaved ownership, "
+                       f"{C} realizations per rank per chunk x {n_chunks} chunks ({padded} generated)",
+           "value_without_gather": padded / (res[False] * 1e-3), "value_with_gather": padded / (res[True] * 1e-3),
+           "ms_without_gather": res[False], "ms_with_gather": res[True], "unit": "realizations/s",
+           "gathered_bytes_per_gpu": b.ld * 8.0 * padded, "gather_overlap": "NCCL all_gather_into_tensor of chunk c on a second stream while "
+           "chunk c+1 is generated (two staging buffers)", "shard_bitwise_ok": bool(ok)}
+    if world > 1:
+        blk["recv_GBps_per_gpu"] = recv / (res[True] * 1e-3) / 1e9
+        blk["nvlink_frac_of_measured_peer_copy"] = blk["recv_GBps_per_gpu"] / NVLINK_PEER_GBS
+        blk["gather_bound_ceiling"] = {"realizations_per_s": padded / (recv / (NVLINK_PEER_GBS * 1e9)),
+                                       "note": f"every GPU must receive (G-1)/G of the result over NVLink: {recv / 1e9:.2f} GB at the measured "
+                                               f"{NVLINK_PEER_GBS:.0f} GB/s peer-copy rate (B200_PROFILING.md)"}
+    del full
+    return blk
+
+
+def bm_variant(lib, args):
+    """Throughput of an alternative Box-Muller build of the library (PTAR_B200_LIB), in a fresh process."""
+    env = dict(os.environ, PTAR_B200_LIB=lib)
+    cmd = [sys.executable, os.path.abspath(__file__), "--steps", "3", "--warmup", "3", "--nreal", str(args.nreal), "--kind", args.kind,
+           "--taylor-tol", str(args.taylor_tol), "--bare"]
+    try:
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+        return {"value": d["value"], "unit": "realizations/s", "roofline_frac": d["roofline"]["frac"], "ms_per_step": d["ms_per_step"]}
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)[:200]}
 
 
 def main():
@@ -120,85 +367,75 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="2", choices=["2", "3", "4", "5", "exact"],
+                    help="BASELINE.json configs: 2 = the metric config (default), 3 = + CGW, 4 = anisotropic lmax 6, "
+                         "5 = ng15-epoch 100k realizations with the overlapped all-gather, exact = config 2 with one epoch per TOA")
     ap.add_argument("--nreal", type=int, default=1000, help="realizations per step per GPU")
     ap.add_argument("--kind", default="full", choices=["full", "epoch"])
     ap.add_argument("--rc", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=0)
-    ap.add_argument("--merged-white", action="store_true", help="one N(0,w1^2+w2^2) draw per TOA instead of two")
+    ap.add_argument("--two-draws", action="store_true", help="two Philox normals per TOA (w1 z1 + w2 z2, like the reference) instead "
+                                                             "of one merged N(0, w1^2+w2^2) draw")
     ap.add_argument("--e2e-nreal", type=int, default=256)
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip other_configs / config5 blocks")
+    ap.add_argument("--bare", action="store_true", help="headline measurement only (used for the library-variant sub-runs)")
     ap.add_argument("--split", action="store_true", help="epoch kernel + TOA kernel (two launches) instead of the fused generator")
     ap.add_argument("--taylor-tol", type=float, default=1e-14,
                     help="PulsarBatch(rn_taylor_tol=...): remainder bound of the in-epoch Taylor step, relative to the red-noise rms")
-    ap.add_argument("--gather", action="store_true", help="also time an NCCL all-gather of one chunk of residuals")
+    ap.add_argument("--c5-nreal", type=int, default=100000)
+    ap.add_argument("--c5-chunk", type=int, default=512)
     args = ap.parse_args()
+    if args.bare:
+        args.no_cpu = args.no_variants = args.no_extras = True
     if args.impl == "reference":
         return run_reference(args)
 
-    import numpy as np
     import torch
     import __graft_entry__ as ge
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    from pta_replicator_b200 import distributed as D
+    affinity0 = os.sched_getaffinity(0)
+    numa = D.bind_to_gpu_numa(local)      # before any pinned allocation: staging buffers on the GPU's NUMA node
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    if rank == 0:
+    if rank == 0 and not os.environ.get("PTAR_B200_LIB"):
         ge.build()               # no-op when the in-tree .so is up to date
     if dist is not None:
         dist.barrier()           # the other ranks load the library only after rank 0 has (re)built it
-    from pta_replicator_b200 import synthetic
-    from pta_replicator_b200.engine import PulsarBatch
 
-    psrs, noise = synthetic.make_ng15_like(args.kind)
-    b = PulsarBatch(psrs, rn_taylor_tol=args.taylor_tol)
-    b.white_merged = bool(args.merged_white)
-    synthetic.ng15_recipe(b, noise)
-    if args.chunk:
-        b.default_chunk = args.chunk
-    b.split_epoch = bool(args.split)
+    cfg = "2" if args.config == "exact" else args.config
+    exact = args.config == "exact"
+    hbm, how = peaks()
+    if cfg == "5":               # config 5 as the headline: value = with the gather
+        blk = config5_block(args, world, rank, dist, hbm)
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": blk["value_with_gather"], "unit": "realizations/s", "n_gpus": world,
+                              "steps": 1, "warmup": 1, "ms_per_step": blk["ms_with_gather"], "higher_is_better": True,
+                              "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                              "config": {"workload": blk["workload"]}, "config5": blk}), flush=True)
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    b, psrs, noise, setup_s, kind = make_batch(cfg, args, merged=not args.two_draws, exact=exact)
     st = b.compile()
     R = args.nreal
-    out = torch.empty((R, b.ld), dtype=torch.float64, device=b.device)
-    out.zero_()
-    seed = 20250922
-
-    def step(k, timers=None):
-        # global realization ids: rank-major blocks so any shard is reproducible on any GPU
-        real0 = ((k * world + rank) * R + 3) // 4 * 4
-        b.generate(R, seed=seed, real0=real0, out=out, rc=args.rc, timers=timers)
-
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()          # samples span warm-up, the timed region and a short soak of the same steps
         t_wait = time.time()
         while not sampler.samples and time.time() - t_wait < 8.0:
             time.sleep(0.05)     # nvidia-smi can take a second to deliver its first sample
-    for k in range(args.warmup):
-        step(k)
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for k in range(args.steps):
-        step(args.warmup + k)
-    e1.record()
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    ms = e0.elapsed_time(e1)
-    # per-kernel durations: the same K steps again, serialized on one stream with CUDA events around every launch
-    timers = {}
-    for k in range(args.steps):
-        step(args.warmup + args.steps + k, timers)
-    torch.cuda.synchronize()
+    ms_max, kern, step = timed_steps(b, R, args.steps, args.warmup, args.rc, world, rank, dist)
     if sampler:
         # the timed region lasts ~10-20 ms, shorter than nvidia-smi's 100 ms period: keep the identical load
         # running for ~0.7 s so that the clock / throttle record is taken under this load
@@ -211,86 +448,78 @@ def main():
         clocks["window"] = "warm-up + timed region + %d soak steps of the same load (%d samples before the soak)" % (k, n0)
     else:
         clocks = None
-    tms = torch.tensor([ms], dtype=torch.float64, device=b.device)
-    if dist is not None:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms_max = float(tms.item())
     value = world * R * args.steps / (ms_max * 1e-3)
-
-    # per-kernel durations inside the timed region (same stream)
-    per = {}
-    for name, a, z in timers["events"]:
-        per.setdefault(name, []).append(a.elapsed_time(z))
-    kern = {k: {"launches": len(v), "avg_ms": float(np.mean(v)), "total_ms": float(np.sum(v))} for k, v in per.items()}
-    chunk_real = min(R, b.default_chunk)
-    hbm, how = peaks()
-    gen = kern["generate"]
-    n_gen = gen["launches"]
-    alg_bytes_per_launch = 8.0 * b.n_toa_total * (R * args.steps / n_gen)
-    achieved = alg_bytes_per_launch / (gen["avg_ms"] * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "gen_kernel (fused white+ECORR+red+GWB-interp generator)", "achieved": achieved,
-            "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None, "peak_source": how,
-            "algorithmic_bytes_per_launch": alg_bytes_per_launch, "avg_launch_ms": gen["avg_ms"],
-            "share_of_step": gen["total_ms"] / sum(k["total_ms"] for k in kern.values())}
-    prof = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.isfile(prof):
-        with open(prof) as fh:
+    roof = roofline_of(b, kern, R, args.steps, hbm, how)
+    n_gen = kern["generate"]["launches"]
+    for prof in sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_traffic.json"))[::-1]:
+        with open(os.path.join(ROOT, "profiles", prof)) as fh:
             tj = json.load(fh)
         cap_real = float(tj.get("gen_kernel_realizations_per_launch", 512))
         cap_bytes = float(tj.get("gen_kernel_dram_bytes_per_launch", 0.0))
         roof["traffic"] = cap_bytes / cap_real * (R * args.steps / n_gen)
-        roof["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of a %d-realization "
-                                "launch (%.4g B; algorithmic %.4g B)%s" % (cap_real, cap_bytes, 8.0 * b.n_toa_total * cap_real,
-                                "" if cap_real == R * args.steps / n_gen else ", scaled to this run's realizations per launch"))
+        stale = tj.get("source_hash") != source_hash()
+        roof["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (profiles/%s) of a %d-realization "
+                                "launch (%.4g B; algorithmic %.4g B), scaled per realization; capture source hash %s, this build %s%s"
+                                % (prof, cap_real, cap_bytes, 8.0 * b.n_toa_total * cap_real, tj.get("source_hash"), source_hash(),
+                                   " -- STALE: the kernels changed since the capture" if stale else ""))
+        roof["traffic_stale"] = bool(stale)
+        break
 
     line = {"metric": METRIC, "value": value, "unit": "realizations/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"ng15-{args.kind}: 67 psr, sum N_toa={b.n_toa_total}, EFAC/EQUAD+ECORR(1s)+RN(30 comp)+HD GWB(npts=600,howml=10)",
-                       "realizations_per_step_per_gpu": R, "rng": "in-kernel Philox4x32-10, fp32 Box-Muller",
-                       "white_draws_per_toa": 1 if args.merged_white else 2, "gwb_chunk": chunk_real,
-                       "rn_taylor_tol": args.taylor_tol,
+            "config": {"workload": workload_name(cfg, kind, b, exact),
+                       "realizations_per_step_per_gpu": R,
+                       "rng": "in-kernel Philox4x32-10 keyed on (seed, global realization id), fp32 MUFU Box-Muller (measured: "
+                              "tests/test_gpu_statistics.py); all residual arithmetic fp64",
+                       "white_draws_per_toa": 2 if args.two_draws else 1, "gwb_chunk": min(R, b.default_chunk),
+                       "rn_taylor_tol": args.taylor_tol, "schedule": "epoch kernel + TOA kernel" if args.split else "fused generator",
                        "l2": f"output per step {R * b.ld * 8 / 1e9:.2f} GB > L2 (126 MB); no flush needed",
-                       "parallelism": f"realization-sharded x{world}, no data-path collective"},
+                       "parallelism": f"realization-sharded x{world}, no data-path collective in `value` (config5 block: with the all-gather)"},
             "kernels": kern, "kernels_timing": "second pass of the same K steps with CUDA events around every launch (same stream, same schedule)",
-            "roofline": roof, "clocks": clocks,
-            "gpu_launches": int(sum(k["launches"] for k in kern.values()))}
+            "roofline": roof, "clocks": clocks, "setup_s": setup_s,
+            "setup_note": "synthetic data set + PulsarBatch + recipe + plan() + compile() (host planning, uploads, Fourier basis, ORF Cholesky, "
+                          "GWB factor QR), once per recipe; not in `value`",
+            "gpu_launches": int(sum(k["launches"] for k in kern.values())), "source_hash": source_hash(), "numa_binding": numa}
 
-    # ---- variant: one merged white draw per TOA (identical distribution; PTAR_F_WHITE1), rank 0, N == 1 only
-    if world == 1 and not args.merged_white and not args.no_variants:
-        b1 = PulsarBatch(psrs, rn_taylor_tol=args.taylor_tol)
-        b1.white_merged = True
-        b1.split_epoch = bool(args.split)
-        synthetic.ng15_recipe(b1, noise)
-        if args.chunk:
-            b1.default_chunk = args.chunk
-        for k in range(2):
-            b1.generate(R, seed=seed, real0=0, out=out, rc=args.rc)
-        tv = {}
-        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        v0.record()
-        for k in range(3):
-            b1.generate(R, seed=seed, real0=4 * R * (k + 1), out=out, rc=args.rc, timers=tv)
-        v1.record()
-        torch.cuda.synchronize()
-        gv = [a.elapsed_time(z) for n, a, z in tv["events"] if n == "generate"]
-        line["variants"] = {"merged_white_draw": {
-            "value": 3 * R / (v0.elapsed_time(v1) * 1e-3), "unit": "realizations/s",
-            "roofline_frac": 8.0 * b.n_toa_total * (3 * R / len(gv)) / (float(np.mean(gv)) * 1e-3) / 1e9 / hbm,
-            "note": "w1 z1 + w2 z2 replaced by sqrt(w1^2+w2^2) z: same Gaussian law, one Philox draw per TOA; not the headline"}}
+    extras = world == 1 and rank == 0 and not args.no_extras
+    # ---- variants (N == 1): the reference's two draws per TOA; library-accurate / float64 Box-Muller builds
+    if world == 1 and not args.no_variants:
+        var = {}
+        b1, *_ = make_batch(cfg, args, merged=bool(args.two_draws), exact=exact, psrs_noise=(psrs, noise))
+        v = short_line(b1, R, args.rc, hbm, how)
+        v["note"] = ("w1 z1 + w2 z2 with two Philox normals per TOA, as the reference consumes them" if not args.two_draws else
+                     "one merged N(0, w1^2 + w2^2) draw per TOA (same Gaussian law)")
+        var["two_white_draws" if not args.two_draws else "merged_white_draw"] = v
         del b1
+        for name, lib in (("box_muller_fp32_accurate", ge.LIB_BM1), ("box_muller_fp64", ge.LIB_BM2)):
+            if os.path.isfile(lib) and not os.environ.get("PTAR_B200_LIB"):
+                var[name] = bm_variant(lib, args)
+        line["variants"] = var
+    if extras:
+        oc = {}
+        for name, c, ex in (("config3_cgw", "3", False), ("config4_aniso_lmax6", "4", False), ("exact_epochs", "2", True)):
+            if (c, ex) == (cfg, exact):
+                continue
+            bb, *_rest = make_batch(c, args, merged=not args.two_draws, exact=ex, psrs_noise=(psrs, noise))
+            Rx = min(R, 256) if ex else R
+            oc[name] = short_line(bb, Rx, args.rc, hbm, how)
+            oc[name]["workload"] = workload_name(c, kind, bb, ex)
+            oc[name]["setup_s"] = _rest[2]
+            del bb
+            torch.cuda.empty_cache()
+        line["other_configs"] = oc
 
     # ---- e2e through the C ABI with host buffers (rank-local; aggregated like `value`)
     Re = min(args.e2e_nreal, R)
     pinned_out = torch.empty((Re, b.ld), dtype=torch.float64, pin_memory=True)
-    host_in = {k: st[k].cpu().pin_memory() for k in ("w1", "w2", "ep_ecorr", "rn_scale")}
+    host_in = {k: st[k].cpu().pin_memory() for k in ("w1", "w2", "wm", "ep_ecorr", "rn_scale") if k in st}
     h2d = int(sum(v.numel() * v.element_size() for v in host_in.values()))
 
     def e2e_step(k):
         for name, h in host_in.items():
             st[name].copy_(h, non_blocking=True)        # this step's noise parameters, pinned host -> device
-        b.generate_to_host(Re, seed=seed + 1, real0=4 * k * Re, out_host=pinned_out, chunk=32, rc=args.rc)
+        b.generate_to_host(Re, seed=SEED + 1, real0=4 * k * Re, out_host=pinned_out, chunk=32, rc=args.rc)
 
     for k in range(2):
         e2e_step(k)
@@ -307,35 +536,20 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     line["e2e"] = {"value": world * Re * ne2e / float(te.item()), "unit": "realizations/s", "h2d_bytes_per_step": h2d,
                    "d2h_bytes_per_step": int(Re * b.ld * 8), "realizations_per_step_per_gpu": Re, "steps": ne2e,
-                   "path": "ptar_run_job_to_host: pinned H2D of noise parameters, generate in chunks of 32, D2H of every residual overlapped on a second stream"}
+                   "d2h_GBps_per_gpu": Re * ne2e * b.ld * 8 / float(te.item()) / 1e9,
+                   "path": "ptar_run_job_to_host: pinned H2D of noise parameters, generate in chunks of 32, D2H of every residual overlapped on a "
+                           "second stream; the process is bound to its GPU's NUMA node before the pinned buffers are allocated"}
+    del pinned_out
 
-    if dist is not None:   # final NCCL all-gather of residuals (north star): timed separately on a bounded block
-        n = min(R, 64)
-        full = torch.empty((world * n, b.ld), dtype=torch.float64, device=b.device)
-        dist.all_gather_into_tensor(full, out[:n])
-        torch.cuda.synchronize()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        dist.all_gather_into_tensor(full, out[:n])
-        g1.record()
-        torch.cuda.synchronize()
-        gms = g0.elapsed_time(g1)
-        gather_rate = world * n / (gms * 1e-3)           # realizations/s the gather alone can deliver to every rank
-        line["allgather"] = {"realizations_per_rank": n, "ms": gms, "recv_GBps_per_gpu": (world - 1) * n * b.ld * 8 / gms / 1e6,
-                             "value_if_every_realization_were_gathered": 1.0 / (1.0 / value + 1.0 / gather_rate),
-                             "note": "final NCCL all_gather_into_tensor of residuals, not in `value`: NVLink moves 8 B/TOA/realization "
-                                     "~6x slower than one GPU generates them; the last key is the serial (un-overlapped) estimate"}
+    if not args.no_extras:
+        del b._bench_out
+        torch.cuda.empty_cache()
+        line["config5"] = config5_block(args, world, rank, dist, hbm)
 
-    # ---- CPU baseline (rank 0, N == 1 only): oracle port on the host cores, bounded sample
+    # ---- CPU baseline (rank 0, N == 1 only): the reference's own code on the host cores, bounded sample
     if rank == 0 and world == 1 and not args.no_cpu:
-        from oracle import recipe
-        ds = recipe.dataset_from_pulsars(psrs, noise)
-        cores = min(os.cpu_count() or 1, 64)
-        _, one = recipe.timed_realizations(ds, 1, 1)
-        v, wall, done = cpu_arm(ds, cores * 4, cores, budget_s=args.cpu_seconds)
-        line["cpu_baseline"] = {"value": v, "unit": "realizations/s", "cores": cores, "kind": "port",
-                                "sample": f"{done} realizations of the same workload in {wall:.1f} s, one single-threaded process per core, "
-                                          f"numpy oracle port (one core alone: {1 / one:.2f}/s); no PINT, no dense U => faster than the unmodified reference"}
+        os.sched_setaffinity(0, affinity0)     # the CPU arm may use every core this process was given
+        line["cpu_baseline"] = cpu_baseline_block(cpu_arms(psrs, noise, args.cpu_seconds))
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:

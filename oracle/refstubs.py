@@ -6,8 +6,11 @@ module top (``/root/reference/pta_replicator/simulate.py:10-20``,
 those is installed here, and none of their arithmetic is on the hot path: they
 carry units and apply ``dt`` to the TOAs.  This module installs ~100 lines of
 ``sys.modules`` stubs and offers a duck-typed pulsar so the five hot functions
-run byte-for-byte as shipped.  It is only usable where ``/root/reference``
-exists (the authoring container); the GPU box uses the committed fixtures.
+run byte-for-byte as shipped.  The package is imported from ``/root/reference``
+where that exists (the authoring container) and otherwise from ``oracle/_ref``,
+the byte-compiled copy staged by ``oracle/build_ref.py`` (git-ignored; it travels
+to the GPU box like a built ``.so``), so the CPU arm of ``bench.py`` times the
+reference's own functions there.
 """
 from __future__ import annotations
 
@@ -17,7 +20,19 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = "/root/reference"
+import os
+
+REFERENCE_ROOT = os.environ.get("PTAR_REFERENCE_ROOT", "/root/reference")   # the override lets a test exercise the staged copy
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def available() -> str:
+    """Where the unmodified reference can be imported from ('' if nowhere)."""
+    if os.path.isdir(os.path.join(REFERENCE_ROOT, "pta_replicator")):
+        return REFERENCE_ROOT
+    if os.path.isfile(os.path.join(STAGED_ROOT, "pta_replicator", "white_noise.pyc")):
+        return STAGED_ROOT
+    return ""
 
 _UNIT_SECONDS = {"s": 1.0, "day": 86400.0, "us": 1e-6, "MHz": 1.0}
 
@@ -166,8 +181,12 @@ def install():
     _module("holodeck", utils=hutils, cosmo=hcosmo)
     cgs = lambda v: types.SimpleNamespace(cgs=types.SimpleNamespace(value=v))  # noqa: E731
     sys.modules["astropy"].constants = _module("astropy.constants", pc=cgs(_H_PC), M_sun=cgs(_H_MSOL))
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    root = available()
+    if not root:
+        raise ImportError("the reference is neither at /root/reference nor staged under oracle/_ref "
+                          "(python -m oracle.build_ref in the authoring container)")
+    if root not in sys.path:
+        sys.path.insert(0, root)
     pkg = importlib.import_module("pta_replicator")
     pkg._ptar_stubbed = True
 
