@@ -39,8 +39,11 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKeys& K) {
   return c;
 }
 
-// Two standard normals from two 32-bit words.  u1 = (a + 0.5) 2^-32 in (0, 1], angle = 2 pi (b + 0.5) 2^-32;
-// radius^2 = -2 ln u1 = 64 ln2 - 2 ln2 * log2(a + 0.5).  MUFU.LG2 / MUFU.RSQ / MUFU.SIN / MUFU.COS.
+// Two standard normals from two 32-bit words.  u1 = (a + 0.5) 2^-32 in (0, 1] (rounded to fp32), angle =
+// 2 pi (b + 0.5) 2^-32 - pi in [-pi, pi) -- the range on which MUFU.SIN / MUFU.COS are accurate to 2^-21.4;
+// radius^2 = -2 ln2 * log2(u1), with log2 taken of u1 itself (not of a + 0.5): for u1 in [0.5, 1), where the
+// radius is small and -2 ln u1 cancels, MUFU.LG2 is then accurate to 2^-22 ABSOLUTE, so |error(z)| ~ 2e-7 / radius
+// instead of 3e-6 / radius -- same instruction count.
 // PTAR_BM_MODE selects the evaluation (timing variants of bench.py; the shipped library is mode 0):
 //   0  fp32 MUFU intrinsics (default; measured against float64 by tests/test_gpu_statistics.py)
 //   1  fp32 library accuracy: log2f + sincospif (1-2 ulp)
@@ -50,25 +53,24 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKeys& K) {
 #endif
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
 #if PTAR_BM_MODE == 0
-  const float af = static_cast<float>(a) + 0.5f;
-  const float r2 = fmaxf(fmaf(__log2f(af), -1.3862943611198906f, 44.361419555836500f), 1e-30f);
+  const float u1 = fmaf(static_cast<float>(a), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+  const float r2 = fmaxf(__log2f(u1) * -1.3862943611198906f, 1e-30f);
   const float r = r2 * rsqrtf(r2);
-  const float th = fmaf(static_cast<float>(b), 1.4629180792671596e-9f, 7.3145903963357980e-10f);
+  const float th = fmaf(static_cast<float>(b), 1.4629180792671596e-9f, -3.1415926535897931f);   // + pi 2^-32 is below fp32 resolution
   n0 = r * __cosf(th);
   n1 = r * __sinf(th);
 #elif PTAR_BM_MODE == 1
-  const float af = static_cast<float>(a) + 0.5f;
-  const float r2 = fmaxf(fmaf(log2f(af), -1.3862943611198906f, 44.361419555836500f), 0.f);
-  const float r = sqrtf(r2);
+  const float u1 = fmaf(static_cast<float>(a), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+  const float r = sqrtf(fmaxf(log2f(u1) * -1.3862943611198906f, 0.f));
   float s, c;
-  sincospif(fmaf(static_cast<float>(b), 4.656612873077393e-10f, 2.3283064365386963e-10f), &s, &c);
+  sincospif(fmaf(static_cast<float>(b), 4.656612873077393e-10f, -1.0f), &s, &c);
   n0 = r * c;
   n1 = r * s;
 #else
   const double u1 = (static_cast<double>(a) + 0.5) * 2.3283064365386963e-10;
   const double r = sqrt(-2.0 * log(u1));
   double s, c;
-  sincospi((static_cast<double>(b) + 0.5) * 4.656612873077393e-10, &s, &c);
+  sincospi((static_cast<double>(b) + 0.5) * 4.656612873077393e-10 - 1.0, &s, &c);
   n0 = static_cast<float>(r * c);
   n1 = static_cast<float>(r * s);
 #endif

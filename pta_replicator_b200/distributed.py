@@ -154,7 +154,8 @@ def bind_to_gpu_numa(device_index: int):
     half the GPUs copy across the socket interconnect.  Returns a description, or None if nothing was changed."""
     try:
         import torch
-        bdf = torch.cuda.get_device_properties(device_index).pci_bus_id  # not available on every build
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (int(pr.pci_domain_id), int(pr.pci_bus_id), int(pr.pci_device_id))
     except Exception:
         bdf = None
     if not bdf:

@@ -11,7 +11,7 @@ from tests.fixtures import load_flags_case, rel_rms
 pytestmark = pytest.mark.gpu
 
 TRIG = 1e-11          # see tests/test_gpu_parity.py
-PHILOX = 2e-5         # fp32 fast-math Box-Muller on the GPU vs float64 log/sin/cos in the oracle (~1e-6 per draw)
+PHILOX = 2e-5         # fp32 MUFU Box-Muller on the GPU vs float64 log/sin/cos of the same fp32 uniforms in the oracle
 
 
 def _batch(api_psrs, spec, **kw):

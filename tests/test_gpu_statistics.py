@@ -25,7 +25,8 @@ from oracle import refnumpy as O
 
 pytestmark = pytest.mark.gpu
 
-PHILOX = 2e-5      # max|d| / rms: fp32 fast-math Box-Muller (GPU) vs float64 Box-Muller of the same uniforms (oracle)
+PHILOX = 5e-5      # max|d| / rms: fp32 MUFU Box-Muller (GPU) vs float64 Box-Muller of the same fp32 uniforms (oracle);
+                   # measured 1.5e-5 (99.99 % of the TOAs: 4.8e-6) on 2.2 M (TOA, realization) pairs
 TAYLOR = 1e-11     # max|d| / rms(red noise of the pulsar): Taylor epochs vs one epoch per TOA, same draws
 
 
@@ -52,8 +53,8 @@ def _batch(ng15, **kw):
 def test_fullsize_throughput_mode_matches_oracle_on_the_same_philox_stream(ng15, merged):
     """ng15-full, all four random terms, 8 realizations: every pulsar of 2 realizations and 12 pulsars of the other
     6 are recomputed by the numpy oracle (oracle/refnumpy.py: white_noise.py:105-109, :182, red_noise.py:126-128,
-    :286-287) from the numpy Philox stream.  Tolerance 2e-5 of the pulsar's rms: the GPU evaluates Box-Muller with
-    fp32 MUFU intrinsics, the oracle in float64 (test_normal_stream_accuracy measures that difference alone)."""
+    :286-287) from the numpy Philox stream.  Tolerance 5e-5 of the pulsar's rms (1e-5 for 99.99 % of the TOAs): the GPU evaluates
+    Box-Muller with fp32 MUFU intrinsics, the oracle in float64 (test_normal_stream_accuracy measures that difference alone)."""
     psrs, noise = ng15
     b = _batch(ng15, merged=merged)
     st = b.compile()
@@ -76,7 +77,7 @@ def test_fullsize_throughput_mode_matches_oracle_on_the_same_philox_stream(ng15,
         ec = O.ecorr_per_bucket(10 ** pp["log10_ecorr"], pp["backends"], flag, firsts)
         static.append((ef, eq, bk, ec, len(firsts)))
     rng = np.random.default_rng(4)
-    worst = 0.0
+    worst, devs = 0.0, []
     for r in range(R):
         rid = real0 + r
         which = range(P) if r < 2 else sorted(rng.choice(P, 12, replace=False))
@@ -98,8 +99,12 @@ def test_fullsize_throughput_mode_matches_oracle_on_the_same_philox_stream(ng15,
             tot = tot + O.red_noise(mjds[i], pp["rn_log10_A"], pp["rn_gamma"], PH.normals(PH.K_RED, i, rid, 60, seed))
             tot = tot + np.interp(mjds[i] * 86400, g["ut"], grid[i])
             got = b.unpack(out[r], i)
-            worst = max(worst, float(np.max(np.abs(got - tot)) / np.sqrt(np.mean(tot ** 2))))
-    assert worst < PHILOX, worst
+            d = np.abs(got - tot) / np.sqrt(np.mean(tot ** 2))
+            worst = max(worst, float(d.max()))
+            devs.append(d)
+    q = float(np.quantile(np.concatenate(devs), 0.9999))
+    print(f"fullsize philox parity merged={merged}: max {worst:.3e}, q99.99 {q:.3e}")
+    assert worst < PHILOX and q < 1e-5, (worst, q)
     del pl
 
 
@@ -157,9 +162,10 @@ def test_normal_stream_tail_counts():
 
 
 def test_normal_stream_accuracy_against_float64_box_muller():
-    """The same uniforms pushed through float64 log / sin / cos (oracle/philox.py): the fp32 MUFU evaluation differs by
-    at most 2.5e-6 on 99.9 % of the draws and by at most 1.2e-3 anywhere; the large differences sit at tiny radii only
-    (u1 -> 1, where -2 ln u1 cancels in fp32), i.e. |z| itself is below 0.05 there."""
+    """The same fp32 uniforms pushed through float64 log / sin / cos (oracle/philox.py): the MUFU evaluation differs by
+    less than 3e-6 on 99.9 % of the draws (measured 1.0e-6; median 1.3e-7) and by less than 2e-4 anywhere (measured
+    6e-5 on 1.3e7 draws); differences above 2e-6 occur only at small radii (|z| < 0.5), where sqrt(-2 ln u1) amplifies
+    the 2^-22 absolute error of MUFU.LG2 as ~2e-7 / radius."""
     n = 1 << 21
     worst, q999 = 0.0, 0.0
     for kind, psr, real, seed in ((1, 0, 0, 1), (2, 66, 123457, 0xDEADBEEFCAFE1234), (5, 12, 99998, 77)):
@@ -167,10 +173,10 @@ def test_normal_stream_accuracy_against_float64_box_muller():
         ref = PH.normals(kind, psr, real, n, seed)
         d = np.abs(got - ref)
         worst, q999 = max(worst, d.max()), max(q999, np.quantile(d, 0.999))
-        big = d > 2e-5
-        assert np.all(np.abs(ref[big]) < 0.05), np.abs(ref[big]).max()
-        assert big.mean() < 2e-4
-    assert q999 < 2.5e-6 and worst < 1.2e-3, (q999, worst)
+        big = d > 2e-6
+        assert np.all(np.abs(ref[big]) < 0.5), np.abs(ref[big]).max()
+    print(f"box-muller accuracy: q99.9 {q999:.3e}, max {worst:.3e}")
+    assert q999 < 3e-6 and worst < 2e-4, (q999, worst)
 
 
 # ------------------------------------------------------------------------------------------------ (c)
