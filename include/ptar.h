@@ -14,6 +14,8 @@
  *   ptar_fourier_basis     create_fourier_design_matrix_red             red_noise.py:36-103
  *   ptar_gwb_mix           w draws + np.dot(M, w)                       red_noise.py:238-240, :268
  *   ptar_gwb_synth         sqrt(C) scale, Hermitian pack, ifft, crop    red_noise.py:269-285
+ *   ptar_gwb_slice_i8 /    the same linear map on the tcgen05 tensor cores (exact int8 digit
+ *   ptar_gwb_synth_i8      slices, int32 TMEM accumulators; throughput mode)   red_noise.py:269-285
  *   ptar_cgw_delay         add_cgw arithmetic                           deterministic.py:98-163
  *   ptar_cw_catalog        loop_over_CWs[_parallel] (numba)             deterministic.py:321-561
  *   ptar_burst_delay       add_burst polarisation mix                   deterministic.py:771-780
@@ -176,6 +178,23 @@ int ptar_gwb_mix(double* Zm, const double* M, const double* zin, int n_psr, int 
 int ptar_gwb_synth(double* G, int64_t g_ld, const double* A, int64_t lda, const double* Zm, int J, int64_t nreal,
                    const int32_t* tile_list, int n_tiles, const int32_t* knots, int lower_tri, void* stream);
 
+/* tcgen05 path of the synthesis (throughput mode; csrc/ptar_gwb_i8.cuh).  Both operands are fixed-point numbers with
+ * PTAR_I8_SLICES signed radix-256 digits: value = scale * sum_s digit_s 2^(-8(s+1)), |value / scale| <= 1/4.
+ * ptar_gwb_slice_i8: Zm[p][r][J] (fp64) -> ZS, int8 digits in the tensor core's K-major core-matrix tile layout
+ *   [slice][pulsar][rcap/128 r-blocks][Jpad/64 k-chunks][16][4][8][16]; zinv[p] = 2^48 / zscale[p]; rcap (multiple of 128)
+ *   is the row capacity the buffer was laid out for (>= nreal), Jpad a multiple of 64 (>= J).
+ * ptar_gwb_synth_i8: G[r][q] = sum_j A[knot(q)][j] Zm[p(q)][r][j] from the digit slices; AS holds the digits of the
+ *   gathered rows of A tile by tile, in tile_list order: [tile][Jpad/64][slice][8][4][8][16]; colscale[q] = (scale of
+ *   row knot(q) of A) * 2^-16; tile_list as in ptar_gwb_synth (64-column blocks; A lower triangular: k stops at the
+ *   tile's k extent).  Exact int8 x int8 -> int32 products on tcgen05.mma.kind::i8; the slice pairs s + t <= 5 are kept
+ *   (dropped weight <= 2^-48), the result is rounded once per output in fp64. */
+#define PTAR_I8_SLICES 6
+int ptar_gwb_slice_i8(int8_t* ZS, const double* Zm, const double* zinv, int n_psr, int J, int Jpad, int64_t nreal,
+                      int64_t rcap, void* stream);
+int ptar_gwb_synth_i8(double* G, int64_t g_ld, const int8_t* AS, const double* colscale, const int8_t* ZS,
+                      const double* zscale, int n_psr, int J, int Jpad, int64_t nreal, int64_t rcap,
+                      const int32_t* tile_list, int n_tiles, void* stream);
+
 /* The fused generator: out[r][i] = white + ecorr + red + gwb + det for nreal realizations. */
 int ptar_generate(const ptar_gen_params* p, void* stream);
 
@@ -209,6 +228,16 @@ typedef struct {
   double* Zm;               /* scratch [n_psr][chunk][Jg]                                 */
   double* Gbuf;             /* scratch [chunk][gen.g_ld]                                  */
   const double* gwb_zin;    /* parity mode: [nreal][n_psr][Jg] or NULL                    */
+  /* tcgen05 synthesis (throughput mode only; all NULL / 0 selects the fp64 DMMA kernel) */
+  const int8_t* AS;         /* digit slices of the gathered rows of A, tile_list_i8 order */
+  const double* colscale;   /* [gen.g_ld]                                                 */
+  int8_t* ZS;               /* scratch: digit slices of Zm, PTAR_I8_SLICES*n_psr*rcap*Jpad bytes */
+  const double* zscale;     /* [n_psr]                                                    */
+  const double* zinv;       /* [n_psr] 2^48 / zscale                                      */
+  const int32_t* tile_list_i8; /* [n_syn_tiles][4], pulsar-major                          */
+  int64_t rcap;             /* row capacity of ZS (multiple of 128, >= chunk)             */
+  int32_t Jpad;             /* multiple of 64, >= Jg                                      */
+  int32_t reserved2;
 } ptar_job;
 
 int ptar_run_job(const ptar_job* job, int64_t real0, int32_t nreal, double* out, void* stream);

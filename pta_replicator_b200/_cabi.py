@@ -16,12 +16,13 @@ LIB_PATH = os.environ.get("PTAR_B200_LIB") or os.path.join(_HERE, "csrc", "libpt
 TILE_TOAS = 1024
 TILE_EPOCHS = 64
 TOA_ALIGN = 4
+I8_SLICES, I8_BM, I8_BN, I8_BK = 6, 128, 64, 64   # tcgen05 GWB synthesis tile (csrc/ptar_gwb_i8.cuh)
 
 F_WHITE, F_ECORR, F_RED, F_GWB, F_DET, F_WHITE1 = 1, 2, 4, 8, 16, 32
 K_WHITE1, K_WHITE2, K_ECORR, K_RED, K_GWB = 1, 2, 3, 4, 5
 
 EXPORTS = ("ptar_version", "ptar_last_error", "ptar_cholesky_lower", "ptar_fourier_basis", "ptar_cgw_delay", "ptar_cw_catalog", "ptar_burst_delay", "ptar_memory_delay",
-           "ptar_gwb_mix", "ptar_gwb_synth", "ptar_generate", "ptar_generate_stage", "ptar_philox_normals", "ptar_run_job",
+           "ptar_gwb_mix", "ptar_gwb_synth", "ptar_gwb_slice_i8", "ptar_gwb_synth_i8", "ptar_generate", "ptar_generate_stage", "ptar_philox_normals", "ptar_run_job",
            "ptar_run_job_to_host")
 
 
@@ -51,7 +52,9 @@ class GenParams(C.Structure):
 class Job(C.Structure):
     _fields_ = [("gen", GenParams), ("M", C.c_void_p), ("A", C.c_void_p), ("lda", C.c_int64), ("Jg", C.c_int32),
                 ("lower_tri", C.c_int32), ("tile_list", C.c_void_p), ("knots", C.c_void_p), ("n_syn_tiles", C.c_int32),
-                ("reserved", C.c_int32), ("Zm", C.c_void_p), ("Gbuf", C.c_void_p), ("gwb_zin", C.c_void_p)]
+                ("reserved", C.c_int32), ("Zm", C.c_void_p), ("Gbuf", C.c_void_p), ("gwb_zin", C.c_void_p),
+                ("AS", C.c_void_p), ("colscale", C.c_void_p), ("ZS", C.c_void_p), ("zscale", C.c_void_p), ("zinv", C.c_void_p),
+                ("tile_list_i8", C.c_void_p), ("rcap", C.c_int64), ("Jpad", C.c_int32), ("reserved2", C.c_int32)]
 
 
 _lib = None
@@ -81,6 +84,8 @@ def lib():
     L.ptar_memory_delay.argtypes = [vp, vp, C.c_double, C.c_double, i32, i64, vp]
     L.ptar_gwb_mix.argtypes = [vp, vp, vp, i32, i32, i64, u64, i64, vp]
     L.ptar_gwb_synth.argtypes = [vp, i64, vp, i64, vp, i32, i64, vp, i32, vp, i32, vp]
+    L.ptar_gwb_slice_i8.argtypes = [vp, vp, vp, i32, i32, i32, i64, i64, vp]
+    L.ptar_gwb_synth_i8.argtypes = [vp, i64, vp, vp, vp, vp, i32, i32, i32, i64, i64, vp, i32, vp]
     L.ptar_generate.argtypes = [C.POINTER(GenParams), vp]
     L.ptar_generate_stage.argtypes = [C.POINTER(GenParams), i32, vp]
     L.ptar_philox_normals.argtypes = [vp, i32, i32, i64, i64, i64, u64, vp]

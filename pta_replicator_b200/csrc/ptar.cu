@@ -9,6 +9,7 @@
 #include "../../include/ptar.h"
 #include "ptar_generate.cuh"
 #include "ptar_gwb.cuh"
+#include "ptar_gwb_i8.cuh"
 #include "ptar_rng.cuh"
 
 namespace {
@@ -403,6 +404,35 @@ int ptar_gwb_synth(double* G, int64_t g_ld, const double* A, int64_t lda, const 
   return check_launch("ptar_gwb_synth");
 }
 
+int ptar_gwb_slice_i8(int8_t* ZS, const double* Zm, const double* zinv, int n_psr, int J, int Jpad, int64_t nreal, int64_t rcap,
+                      void* stream) {
+  if (!ZS || !Zm || !zinv || n_psr <= 0 || J <= 0 || nreal <= 0) return fail(-1, "ptar_gwb_slice_i8: bad argument%s");
+  if (Jpad < J || (Jpad % ptar::I8_BK) || rcap < nreal || (rcap % ptar::I8_BM))
+    return fail(-2, "ptar_gwb_slice_i8: need Jpad %% 64 == 0 >= J and rcap %% 128 == 0 >= nreal%s");
+  const int64_t total = ((nreal + 7) / 8) * (Jpad / 16) * 8 * n_psr;
+  ptar::gwb_slice_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      ZS, Zm, zinv, n_psr, J, Jpad, nreal, rcap);
+  return check_launch("ptar_gwb_slice_i8");
+}
+
+int ptar_gwb_synth_i8(double* G, int64_t g_ld, const int8_t* AS, const double* colscale, const int8_t* ZS, const double* zscale,
+                      int n_psr, int J, int Jpad, int64_t nreal, int64_t rcap, const int32_t* tile_list, int n_tiles,
+                      void* stream) {
+  if (!G || !AS || !colscale || !ZS || !zscale || !tile_list || n_psr <= 0 || J <= 0 || nreal <= 0 || n_tiles <= 0 || g_ld <= 0)
+    return fail(-1, "ptar_gwb_synth_i8: bad argument%s");
+  if (Jpad < J || (Jpad % ptar::I8_BK) || rcap < nreal || (rcap % ptar::I8_BM) || (g_ld & 1))
+    return fail(-2, "ptar_gwb_synth_i8: need Jpad %% 64 == 0 >= J, rcap %% 128 == 0 >= nreal, even g_ld%s");
+  if ((reinterpret_cast<uintptr_t>(AS) | reinterpret_cast<uintptr_t>(ZS)) & 15)
+    return fail(-2, "ptar_gwb_synth_i8: AS / ZS must be 16-byte aligned%s");
+  if (n_tiles > 65535) return fail(-3, "ptar_gwb_synth_i8: more than 65535 tiles%s");
+  static SmemOptIn optin;
+  if (int rc = opt_in_smem(ptar::gwb_synth_i8_kernel, optin, ptar::I8_SMEM, "ptar_gwb_synth_i8")) return rc;
+  const dim3 grid(static_cast<unsigned>((nreal + ptar::I8_BM - 1) / ptar::I8_BM), static_cast<unsigned>(n_tiles));
+  ptar::gwb_synth_i8_kernel<<<grid, ptar::I8_THREADS, ptar::I8_SMEM, static_cast<cudaStream_t>(stream)>>>(
+      G, g_ld, AS, colscale, ZS, zscale, n_psr, J, Jpad, nreal, rcap, tile_list);
+  return check_launch("ptar_gwb_synth_i8");
+}
+
 int ptar_generate(const ptar_gen_params* pp, void* stream) {
   if (!pp) return fail(-1, "ptar_generate: null params%s");
   const ptar_gen_params& p = *pp;
@@ -483,8 +513,17 @@ int ptar_run_job(const ptar_job* job, int64_t real0, int32_t nreal, double* out,
       return fail(-2, "ptar_run_job: GWB buffers missing%s");
     int rc = ptar_gwb_mix(job->Zm, job->M, inject ? job->gwb_zin : nullptr, g.n_psr, job->Jg, nreal, g.seed, real0, stream);
     if (rc) return rc;
-    rc = ptar_gwb_synth(job->Gbuf, g.g_ld, job->A, job->lda, job->Zm, job->Jg, nreal, job->tile_list, job->n_syn_tiles,
-                        job->knots, job->lower_tri, stream);
+    if (job->AS && !inject) {   // tcgen05 path: digit slices of Zm, exact int8 GEMMs, fp64 fix-up
+      if (!job->ZS || !job->colscale || !job->zscale || !job->zinv || !job->tile_list_i8)
+        return fail(-2, "ptar_run_job: tcgen05 GWB buffers missing%s");
+      rc = ptar_gwb_slice_i8(job->ZS, job->Zm, job->zinv, g.n_psr, job->Jg, job->Jpad, nreal, job->rcap, stream);
+      if (rc) return rc;
+      rc = ptar_gwb_synth_i8(job->Gbuf, g.g_ld, job->AS, job->colscale, job->ZS, job->zscale, g.n_psr, job->Jg, job->Jpad, nreal,
+                             job->rcap, job->tile_list_i8, job->n_syn_tiles, stream);
+    } else {
+      rc = ptar_gwb_synth(job->Gbuf, g.g_ld, job->A, job->lda, job->Zm, job->Jg, nreal, job->tile_list, job->n_syn_tiles,
+                          job->knots, job->lower_tri, stream);
+    }
     if (rc) return rc;
     g.G = job->Gbuf;
   }

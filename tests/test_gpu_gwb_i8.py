@@ -1,0 +1,109 @@
+"""GPU tests of the tcgen05 GWB synthesis (csrc/ptar_gwb_i8.cuh; ptar_gwb_slice_i8 + ptar_gwb_synth_i8): exact int8
+digit-slice GEMMs with int32 TMEM accumulators against the fp64 DMMA kernel (ptar_gwb_synth) on the SAME mixed draws,
+the digit slices against the host restatement, and the end-to-end generator with either synthesis.
+
+Tolerance I8 = 1e-12 of the rms of the grid signal: operands carry 46-48 bits relative to their row maximum, the
+dropped slice pairs weigh 2^-48, and the DMMA reference itself accumulates 600 fp64 products (~1e-15 each)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+I8 = 1e-12
+
+
+def _gwb_batch(npsr=None, kind="full"):
+    from pta_replicator_b200 import synthetic
+    from pta_replicator_b200.engine import PulsarBatch
+    psrs, noise = synthetic.make_ng15_like(kind, npsr=npsr)
+    b = PulsarBatch(psrs)
+    b.set_gwb(-14.6733, 13.0 / 3.0)
+    return b
+
+
+def _both_syntheses(b, R, seed=5, real0=8):
+    """Zm from the Philox mix, then G by the DMMA kernel and by the tcgen05 kernels."""
+    import torch
+    from pta_replicator_b200 import _cabi
+    L = _cabi.lib()
+    st = b.compile()
+    job, keep = b._job(st, R, seed, None, 0)
+    stream = _cabi.current_stream()
+    _cabi.check(L.ptar_gwb_mix(job.Zm, job.M, None, b.n_psr, job.Jg, R, seed, real0, stream), "mix")
+    Gd = torch.zeros(R * st["g_ld"], dtype=torch.float64, device=b.device)
+    Gi = torch.full((R * st["g_ld"],), float("nan"), dtype=torch.float64, device=b.device)
+    _cabi.check(L.ptar_gwb_synth(Gd.data_ptr(), st["g_ld"], job.A, job.lda, job.Zm, job.Jg, R, job.tile_list, job.n_syn_tiles,
+                                 job.knots, job.lower_tri, stream), "synth")
+    _cabi.check(L.ptar_gwb_slice_i8(job.ZS, job.Zm, job.zinv, b.n_psr, job.Jg, job.Jpad, R, job.rcap, stream), "slice")
+    _cabi.check(L.ptar_gwb_synth_i8(Gi.data_ptr(), st["g_ld"], job.AS, job.colscale, job.ZS, job.zscale, b.n_psr, job.Jg, job.Jpad,
+                                    R, job.rcap, job.tile_list_i8, job.n_syn_tiles, stream), "synth_i8")
+    torch.cuda.synchronize()
+    return Gd.view(R, -1), Gi.view(R, -1), job, keep, st
+
+
+@pytest.mark.parametrize("npsr,R", [(3, 40), (5, 200), (67, 256)])
+def test_tcgen05_synthesis_matches_the_fp64_tensor_kernel(npsr, R):
+    """Ragged realization counts (not a multiple of the 128-row MMA tile), few and all pulsars."""
+    import torch
+    b = _gwb_batch(npsr)
+    Gd, Gi, job, keep, st = _both_syntheses(b, R)
+    knots = st["knots"].cpu().numpy()
+    valid = torch.from_numpy(knots >= 0).to(Gd.device)
+    assert torch.isfinite(Gi[:, valid]).all()
+    rms = Gd[:, valid].std().item()
+    err = (Gi[:, valid] - Gd[:, valid]).abs().max().item() / rms
+    print(f"tcgen05 vs DMMA synthesis, {npsr} psr x {R}: max|d|/rms = {err:.3e}")
+    assert err < I8, err
+    # pad columns (odd pulsar blocks) are written as zeros by both kernels
+    assert (Gi[:, ~valid].nan_to_num(0.0) == 0).all()
+
+
+def test_digit_slices_match_the_host_restatement():
+    """ptar_gwb_slice_i8 against PulsarBatch.radix256_digits for one (pulsar, r-block, k-chunk) tile, and the
+    reconstruction sum_s d_s 2^(-8(s+1)) * zscale == Zm to 2^-47 of zscale."""
+    import torch
+    from pta_replicator_b200 import _cabi
+    from pta_replicator_b200.engine import PulsarBatch
+    b = _gwb_batch(4)
+    R = 136
+    Gd, Gi, job, keep, st = _both_syntheses(b, R)
+    P, Jg, Jpad, rcap = b.n_psr, job.Jg, job.Jpad, job.rcap
+    Zm = [k for k in keep if k.dtype == torch.float64 and k.numel() == R * P * Jg][0].view(P, R, Jg).cpu().numpy()
+    ZS = [k for k in keep if k.dtype == torch.int8][0].cpu().numpy()
+    ZS = ZS.reshape(_cabi.I8_SLICES, P, rcap // 128, Jpad // 64, 16, 4, 8, 16)
+    zscale = st["i8_zscale"].cpu().numpy()
+    for p in (0, P - 1):
+        for rblk, kch in ((0, 0), (1, 9), (0, 4)):
+            tile = ZS[:, p, rblk, kch]                                  # [s][g][c][r8][16]
+            dig = tile.transpose(0, 1, 3, 2, 4).reshape(_cabi.I8_SLICES, 128, 64)   # [s][row][k]
+            rows = np.arange(rblk * 128, min(rblk * 128 + 128, R))
+            cols = np.arange(kch * 64, min(kch * 64 + 64, Jg))
+            x = np.zeros((128, 64))
+            x[:len(rows), :len(cols)] = Zm[p][rows][:, cols] / zscale[p]
+            ref = PulsarBatch.radix256_digits(x)
+            assert np.array_equal(dig[:, :len(rows)], ref[:, :len(rows)]), (p, rblk, kch)
+            rec = sum(dig[s].astype(np.float64) * 2.0 ** (-8 * (s + 1)) for s in range(_cabi.I8_SLICES))
+            assert np.abs(rec - x)[:len(rows)].max() <= 2.0 ** -48
+            assert np.abs(x).max() <= 0.25
+
+
+@pytest.mark.parametrize("kind", ["full", "epoch"])
+def test_generator_with_tcgen05_synthesis_equals_the_fp64_path(kind):
+    """End to end (all signals, Philox mode, chunked): use_tcgen05 True vs False on the same seed, every pulsar."""
+    from pta_replicator_b200 import synthetic
+    from pta_replicator_b200.engine import PulsarBatch
+    psrs, noise = synthetic.make_ng15_like(kind)
+    b = PulsarBatch(psrs)
+    synthetic.ng15_recipe(b, noise)
+    b.default_chunk = 192                      # two chunks: 192 + 108 realizations (ragged r-block)
+    R = 300
+    b.use_tcgen05 = False
+    ref = b.generate(R, seed=77, real0=16)
+    b.use_tcgen05 = True
+    got = b.generate(R, seed=77, real0=16)
+    worst = 0.0
+    for i in range(b.n_psr):
+        sl = slice(b.toa_off[i], b.toa_off[i] + b.ntoa[i])
+        worst = max(worst, ((got[:, sl] - ref[:, sl]).abs().max() / ref[:, sl].std()).item())
+    print(f"generator with tcgen05 synthesis vs fp64 ({kind}): max|d|/rms = {worst:.3e}")
+    assert worst < I8, worst
