@@ -186,9 +186,13 @@ int ptar_gwb_synth(double* G, int64_t g_ld, const double* A, int64_t lda, const 
  * ptar_gwb_synth_i8: G[r][q] = sum_j A[knot(q)][j] Zm[p(q)][r][j] from the digit slices; AS holds the digits of the
  *   gathered rows of A tile by tile, in tile_list order: [tile][Jpad/64][slice][8][4][8][16]; colscale[q] = (scale of
  *   row knot(q) of A) * 2^-16; tile_list as in ptar_gwb_synth (64-column blocks; A lower triangular: k stops at the
- *   tile's k extent).  Exact int8 x int8 -> int32 products on tcgen05.mma.kind::i8; the slice pairs s + t <= 5 are kept
- *   (dropped weight <= 2^-48), the result is rounded once per output in fp64. */
+ *    tile's k extent).  Exact int8 x int8 -> int32 products on tcgen05.mma.kind::i8; the slice pairs s + t <= 6 are kept
+ *   (dropped weight <= 2^-56 of full scale), the result is rounded once per output in fp64.
+ * ptar_gwb_mix_i8: ptar_gwb_mix (Philox draws) with the slicing fused into its epilogue: ZS directly, no fp64 Zm
+ *   (n_psr <= 72; larger arrays use ptar_gwb_mix + ptar_gwb_slice_i8). */
 #define PTAR_I8_SLICES 6
+int ptar_gwb_mix_i8(int8_t* ZS, const double* M, const double* zinv, int n_psr, int J, int Jpad, int64_t nreal, int64_t rcap,
+                    uint64_t seed, int64_t real0, void* stream);
 int ptar_gwb_slice_i8(int8_t* ZS, const double* Zm, const double* zinv, int n_psr, int J, int Jpad, int64_t nreal,
                       int64_t rcap, void* stream);
 int ptar_gwb_synth_i8(double* G, int64_t g_ld, const int8_t* AS, const double* colscale, const int8_t* ZS,

@@ -297,6 +297,23 @@ int launch_gen(const ptar_gen_params& p, cudaStream_t st) {
   return launch_stage<RC, INJECT, WHITE, DET, 0>(p, st);
 }
 
+template <bool INJECT, bool SLICE>
+int launch_mix(double* Zm, const double* M, const double* zin, int n_psr, int J, int64_t nreal, uint64_t seed, int64_t real0,
+               int8_t* ZS, const double* zinv, int Jpad, int64_t rcap, cudaStream_t st, const char* what) {
+  const dim3 grid((J + ptar::MIX_JT - 1) / ptar::MIX_JT,
+                  static_cast<unsigned>((nreal + 4 * ptar::MX_GROUPS - 1) / (4 * ptar::MX_GROUPS)));
+  if (grid.y > 65535) return fail(-3, "ptar_gwb_mix: more than 262140 realizations per call%s");
+  const int KP = (n_psr + 3) & ~3, NP = (n_psr + 7) & ~7;
+  // draws [KP][132] + M [NP][KP + 4] doubles: 113 KB at 67 pulsars (2 CTAs per SM), the 227 KB limit is reached at 115 pulsars
+  const size_t smem = sizeof(double) * (size_t(KP) * ptar::MX_ZS + size_t(NP) * (KP + 4));
+  if (smem > 227 * 1024) return fail(-3, "ptar_gwb_mix: more than 115 pulsars do not fit the shared-memory tile%s");
+  static SmemOptIn optin;   // per instantiation
+  if (int rc = opt_in_smem(ptar::gwb_mix_dmma_kernel<INJECT, SLICE>, optin, 227 * 1024, what)) return rc;
+  ptar::gwb_mix_dmma_kernel<INJECT, SLICE><<<grid, 256, smem, st>>>(Zm, M, zin, n_psr, J, nreal, ptar::philox_keys(seed), real0, ZS,
+                                                                     zinv, Jpad, rcap);
+  return check_launch(what);
+}
+
 }  // namespace
 
 extern "C" {
@@ -372,21 +389,19 @@ int ptar_gwb_mix(double* Zm, const double* M, const double* zin, int n_psr, int 
   if (!Zm || !M || n_psr <= 0 || J <= 0 || nreal <= 0) return fail(-1, "ptar_gwb_mix: bad argument%s");
   if (!zin && (real0 & 3)) return fail(-2, "ptar_gwb_mix: real0 must be a multiple of 4%s");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const dim3 grid((J + ptar::MIX_JT - 1) / ptar::MIX_JT,
-                  static_cast<unsigned>((nreal + 4 * ptar::MX_GROUPS - 1) / (4 * ptar::MX_GROUPS)));
-  const int KP = (n_psr + 3) & ~3, NP = (n_psr + 7) & ~7;
-  const size_t smem = sizeof(double) * (size_t(KP) * ptar::MX_ZS + size_t(NP) * (KP + 4));
-  if (smem > 227 * 1024) return fail(-3, "ptar_gwb_mix: too many pulsars for shared memory%s");
-  if (zin) {
-    static SmemOptIn optin;
-    if (int rc = opt_in_smem(ptar::gwb_mix_dmma_kernel<true>, optin, 227 * 1024, "ptar_gwb_mix")) return rc;
-    ptar::gwb_mix_dmma_kernel<true><<<grid, 256, smem, st>>>(Zm, M, zin, n_psr, J, nreal, ptar::philox_keys(seed), real0);
-  } else {
-    static SmemOptIn optin;
-    if (int rc = opt_in_smem(ptar::gwb_mix_dmma_kernel<false>, optin, 227 * 1024, "ptar_gwb_mix")) return rc;
-    ptar::gwb_mix_dmma_kernel<false><<<grid, 256, smem, st>>>(Zm, M, zin, n_psr, J, nreal, ptar::philox_keys(seed), real0);
-  }
-  return check_launch("ptar_gwb_mix");
+  if (zin) return launch_mix<true, false>(Zm, M, zin, n_psr, J, nreal, seed, real0, nullptr, nullptr, 0, 0, st, "ptar_gwb_mix");
+  return launch_mix<false, false>(Zm, M, zin, n_psr, J, nreal, seed, real0, nullptr, nullptr, 0, 0, st, "ptar_gwb_mix");
+}
+
+int ptar_gwb_mix_i8(int8_t* ZS, const double* M, const double* zinv, int n_psr, int J, int Jpad, int64_t nreal, int64_t rcap,
+                    uint64_t seed, int64_t real0, void* stream) {
+  if (!ZS || !M || !zinv || n_psr <= 0 || J <= 0 || nreal <= 0) return fail(-1, "ptar_gwb_mix_i8: bad argument%s");
+  if (n_psr > 8 * ptar::MX_MAXNT) return fail(-3, "ptar_gwb_mix_i8: more than 72 pulsars (use ptar_gwb_mix + ptar_gwb_slice_i8)%s");
+  if (real0 & 3) return fail(-2, "ptar_gwb_mix_i8: real0 must be a multiple of 4%s");
+  if (Jpad < J || (Jpad % ptar::I8_BK) || rcap < nreal || (rcap % ptar::I8_BM))
+    return fail(-2, "ptar_gwb_mix_i8: need Jpad %% 64 == 0 >= J and rcap %% 128 == 0 >= nreal%s");
+  return launch_mix<false, true>(nullptr, M, nullptr, n_psr, J, nreal, seed, real0, ZS, zinv, Jpad, rcap, static_cast<cudaStream_t>(stream),
+                                 "ptar_gwb_mix_i8");
 }
 
 int ptar_gwb_synth(double* G, int64_t g_ld, const double* A, int64_t lda, const double* Zm, int J, int64_t nreal,
@@ -511,13 +526,21 @@ int ptar_run_job(const ptar_job* job, int64_t real0, int32_t nreal, double* out,
   if (g.flags & PTAR_F_GWB) {
     if (!job->M || !job->A || !job->Zm || !job->Gbuf || !job->tile_list || !job->knots)
       return fail(-2, "ptar_run_job: GWB buffers missing%s");
-    int rc = ptar_gwb_mix(job->Zm, job->M, inject ? job->gwb_zin : nullptr, g.n_psr, job->Jg, nreal, g.seed, real0, stream);
+    const bool i8 = job->AS && !inject;
+    int rc = 0;
+    if (i8 && g.n_psr <= 8 * ptar::MX_MAXNT) {   // mixing emits the digit slices directly
+      if (!job->ZS || !job->zinv) return fail(-2, "ptar_run_job: tcgen05 GWB buffers missing%s");
+      rc = ptar_gwb_mix_i8(job->ZS, job->M, job->zinv, g.n_psr, job->Jg, job->Jpad, nreal, job->rcap, g.seed, real0, stream);
+    } else {
+      rc = ptar_gwb_mix(job->Zm, job->M, inject ? job->gwb_zin : nullptr, g.n_psr, job->Jg, nreal, g.seed, real0, stream);
+      if (!rc && i8) {
+        if (!job->ZS || !job->zinv) return fail(-2, "ptar_run_job: tcgen05 GWB buffers missing%s");
+        rc = ptar_gwb_slice_i8(job->ZS, job->Zm, job->zinv, g.n_psr, job->Jg, job->Jpad, nreal, job->rcap, stream);
+      }
+    }
     if (rc) return rc;
-    if (job->AS && !inject) {   // tcgen05 path: digit slices of Zm, exact int8 GEMMs, fp64 fix-up
-      if (!job->ZS || !job->colscale || !job->zscale || !job->zinv || !job->tile_list_i8)
-        return fail(-2, "ptar_run_job: tcgen05 GWB buffers missing%s");
-      rc = ptar_gwb_slice_i8(job->ZS, job->Zm, job->zinv, g.n_psr, job->Jg, job->Jpad, nreal, job->rcap, stream);
-      if (rc) return rc;
+    if (i8) {   // tcgen05 path: exact int8 GEMMs on the digit slices, fp64 fix-up
+      if (!job->colscale || !job->zscale || !job->tile_list_i8) return fail(-2, "ptar_run_job: tcgen05 GWB buffers missing%s");
       rc = ptar_gwb_synth_i8(job->Gbuf, g.g_ld, job->AS, job->colscale, job->ZS, job->zscale, g.n_psr, job->Jg, job->Jpad, nreal,
                              job->rcap, job->tile_list_i8, job->n_syn_tiles, stream);
     } else {

@@ -36,10 +36,21 @@ namespace ptar {
 // Warp w owns rows 16w..16w+15 (2 m-tiles) and all n-tiles; k-steps above the diagonal are skipped.
 constexpr int MIX_JT = 32, MX_ROWS = 128, MX_ZS = MX_ROWS + 4, MX_GROUPS = 1;
 
-template <bool INJECT>
-__global__ void __launch_bounds__(256) gwb_mix_dmma_kernel(double* __restrict__ Zm, const double* __restrict__ M,
-                                                            const double* __restrict__ zin, int P, int J,
-                                                            int64_t nreal, const PhiloxKeys K, int64_t real0) {
+// SLICE = true (throughput mode with the tcgen05 synthesis, n_psr <= 72): instead of fp64 Zm the kernel emits the
+// six signed radix-256 digit slices of Zm[p][r][j] / zscale[p] in the tensor core's K-major core-matrix tile layout
+// (ptar_gwb_i8.cuh: ZS[slice][p][r-block][k-chunk][16][4][8][16]).  The accumulators of all n-tiles stay in registers,
+// the digits are staged through the shared memory the draws occupied and leave as 16-byte stores.  Digit
+// extraction: m = fma(v, 2^48 / zscale, 1.5 * 2^52) holds round(v 2^48 / zscale) in its low mantissa bits; adding
+// 0x80 to every byte position turns the balanced digits d in [-128, 127] into the plain bytes d + 128 of that integer.
+constexpr int MX_MAXNT = 9;                    // n-tiles kept in registers by the SLICE build (n_psr <= 72)
+constexpr int MX_DSTRIDE = 6 * 2 * 4 * 16 + 16;  // bytes per pulsar in the digit staging area (+16: bank skew)
+
+template <bool INJECT, bool SLICE>
+__global__ void __launch_bounds__(256, 2) gwb_mix_dmma_kernel(double* __restrict__ Zm, const double* __restrict__ M,
+                                                               const double* __restrict__ zin, int P, int J,
+                                                               int64_t nreal, const PhiloxKeys K, int64_t real0,
+                                                               int8_t* __restrict__ ZS, const double* __restrict__ zinv,
+                                                               int Jpad, int64_t rcap) {
   extern __shared__ __align__(16) double mx_smem[];
   const int KP = (P + 3) & ~3, NP = (P + 7) & ~7, MS = KP + 4;
   double* zs = mx_smem;                       // [KP][132]
@@ -76,7 +87,10 @@ __global__ void __launch_bounds__(256) gwb_mix_dmma_kernel(double* __restrict__ 
       for (int l = 0; l < 4; ++l) zs[size_t(q) * MX_ZS + l * MIX_JT + jj] = z[l];
     }
     __syncthreads();
-    for (int nt = 0; nt < n_nt; ++nt) {
+    double keep[SLICE ? MX_MAXNT : 1][2][2];
+#pragma unroll
+    for (int nt = 0; nt < (SLICE ? MX_MAXNT : 16); ++nt) {
+      if (nt >= n_nt) break;
       double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
       const int kmax = min(KP, (nt * 8 + 8 + 3) & ~3);  // q <= p < nt*8+8
       for (int k0 = 0; k0 < kmax; k0 += 4) {
@@ -86,16 +100,65 @@ __global__ void __launch_bounds__(256) gwb_mix_dmma_kernel(double* __restrict__ 
         PTAR_DMMA(acc[0][0], acc[0][1], a0, b);
         PTAR_DMMA(acc[1][0], acc[1][1], a1, b);
       }
+      if (SLICE) {
+        keep[nt][0][0] = acc[0][0]; keep[nt][0][1] = acc[0][1]; keep[nt][1][0] = acc[1][0]; keep[nt][1][1] = acc[1][1];
+      } else {
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const int row = row0 + t * 8 + fr;
-        const int l = row >> 5, jj = row & 31, j = j0 + jj;
-        if (j < J && rbase + l < nreal) {
+        for (int t = 0; t < 2; ++t) {
+          const int row = row0 + t * 8 + fr;
+          const int l = row >> 5, jj = row & 31, j = j0 + jj;
+          if (j < J && rbase + l < nreal) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int p = nt * 8 + 2 * fk + u;
+              if (p < P) Zm[(size_t(p) * nreal + (rbase + l)) * J + j] = acc[t][u];
+            }
+          }
+        }
+      }
+    }
+    if (SLICE) {
+      __syncthreads();                                   // every warp is done reading the draws
+      unsigned char* ds = reinterpret_cast<unsigned char*>(zs);   // [p][slice][c][l][16] (+ skew)
+#pragma unroll
+      for (int nt = 0; nt < MX_MAXNT; ++nt) {
+        if (nt >= n_nt) break;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int row = row0 + t * 8 + fr;
+          const int l = row >> 5, jj = row & 31;
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             const int p = nt * 8 + 2 * fk + u;
-            if (p < P) Zm[(size_t(p) * nreal + (rbase + l)) * J + j] = acc[t][u];
+            if (p < P) {
+              const double m = fma(keep[nt][t][u], __ldg(zinv + p), 6755399441055744.0);   // 1.5 * 2^52
+              // low 48 bits of the mantissa = round(v * zinv) in two's complement; + 0x80 per byte -> bytes d + 128
+              const unsigned long long xb = static_cast<unsigned long long>(__double_as_longlong(m)) + 0x0000808080808080ull;
+              const uint32_t lo = static_cast<uint32_t>(xb) ^ 0x80808080u;            // digits of slices 5, 4, 3, 2
+              const uint32_t hi = static_cast<uint32_t>(xb >> 32) ^ 0x00008080u;      // digits of slices 1, 0
+              unsigned char* d = ds + size_t(p) * MX_DSTRIDE + ((jj >> 4) * 4 + l) * 16 + (jj & 15);
+              d[5 * 128] = static_cast<unsigned char>(lo);
+              d[4 * 128] = static_cast<unsigned char>(lo >> 8);
+              d[3 * 128] = static_cast<unsigned char>(lo >> 16);
+              d[2 * 128] = static_cast<unsigned char>(lo >> 24);
+              d[1 * 128] = static_cast<unsigned char>(hi);
+              d[0 * 128] = static_cast<unsigned char>(hi >> 8);
+            }
           }
+        }
+      }
+      __syncthreads();
+      // 16-byte pieces: (p, slice, c, l) -> ZS[slice][p][rblk][kch][g][c][r8][16]; the four rows of a piece are adjacent
+      const int64_t n_rblk = rcap / 128, nkch = Jpad / 64;
+      const int kch = j0 / 64, c0 = (j0 % 64) / 16;
+      const int64_t rblk = rbase / 128;
+      const int g = static_cast<int>((rbase % 128) / 8), r8 = static_cast<int>(rbase % 8);
+      for (int idx = tid; idx < P * 6 * 2 * 4; idx += 256) {
+        const int l = idx & 3, c = (idx >> 2) & 1, sl = (idx >> 3) % 6, p = idx / 48;
+        const uint4 v = *reinterpret_cast<const uint4*>(ds + size_t(p) * MX_DSTRIDE + ((sl * 2 + c) * 4 + l) * 16);
+        if (rbase + l < rcap && j0 + c * 16 < Jpad) {
+          int8_t* dst = ZS + ((((size_t(sl) * P + p) * n_rblk + rblk) * nkch + kch) * 16 + g) * 512 + ((c0 + c) * 8 + r8 + l) * 16;
+          *reinterpret_cast<uint4*>(dst) = v;
         }
       }
     }
