@@ -199,6 +199,11 @@ int ptar_gwb_synth_i8(double* G, int64_t g_ld, const int8_t* AS, const double* c
                       const double* zscale, int n_psr, int J, int Jpad, int64_t nreal, int64_t rcap,
                       const int32_t* tile_list, int n_tiles, void* stream);
 
+/* Diagnostics: buf (device, n_tiles * 8 int64, or NULL to switch off) receives clock64() stamps of the phases of
+ * ptar_gwb_synth_i8 for the CTAs of r-block 0 (start, setup, loads issued, first stage landed, MMAs issued,
+ * accumulators complete, epilogue done, k-chunks); used by tools/i8_timeline.py. */
+int ptar_debug_i8_timestamps(void* buf);
+
 /* The fused generator: out[r][i] = white + ecorr + red + gwb + det for nreal realizations. */
 int ptar_generate(const ptar_gen_params* p, void* stream);
 

@@ -448,6 +448,12 @@ int ptar_gwb_synth_i8(double* G, int64_t g_ld, const int8_t* AS, const double* c
   return check_launch("ptar_gwb_synth_i8");
 }
 
+int ptar_debug_i8_timestamps(void* buf) {
+  const cudaError_t e = cudaMemcpyToSymbol(ptar::g_i8_dbg, &buf, sizeof(buf));
+  if (e != cudaSuccess) return fail(-100, "ptar_debug_i8_timestamps: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 int ptar_generate(const ptar_gen_params* pp, void* stream) {
   if (!pp) return fail(-1, "ptar_generate: null params%s");
   const ptar_gen_params& p = *pp;

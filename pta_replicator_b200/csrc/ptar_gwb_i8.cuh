@@ -22,8 +22,9 @@
 // per slice, split at N = 256) and lands in TMEM columns 64 (s + t) + knot: the stacking along N is what makes the
 // 26 slice products cost 9 instructions per 32-j step instead of 26.
 //
-// CTA = 192 threads: warp 0 lane 0 issues the bulk copies (3-stage mbarrier ring, 72 KB per stage), warp 1 allocates
-// TMEM (512 columns) and its lane 0 issues the MMAs, warps 2-5 run the epilogue (warp w reads TMEM lanes 32 (w % 4)..).
+// CTA = 256 threads: warp 0 lane 0 issues the bulk copies (3-stage mbarrier ring, 72 KB per stage), warp 1 allocates
+// TMEM (512 columns) and its lane 0 issues the MMAs; then all 8 warps run the epilogue (warp w reads TMEM lanes
+// 32 (w % 4).. and the knots 32 (w / 4)..).  Measured phase times per CTA: tools/i8_timeline.py.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -40,7 +41,7 @@ constexpr int I8_A_BYTES = I8_BM * I8_BK;                 // one Z slice of one 
 constexpr int I8_B_BYTES = I8_SLICES * I8_BN * I8_BK;     // all A slices of one stage: 24 KB
 constexpr int I8_STAGE_BYTES = I8_SLICES * I8_A_BYTES + I8_B_BYTES;   // 72 KB
 constexpr int I8_TMEM_COLS = 512;                         // 7 diagonals x 64 knots = 448 used
-constexpr int I8_THREADS = 192;
+constexpr int I8_THREADS = 256;
 constexpr size_t I8_SMEM = size_t(I8_STAGES) * I8_STAGE_BYTES + 128;   // + barriers, tmem address
 
 __device__ __forceinline__ uint32_t i8_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -141,6 +142,11 @@ __global__ void __launch_bounds__(256) gwb_slice_kernel(int8_t* __restrict__ ZS,
   }
 }
 
+// Diagnostics (ptar_debug_i8_timestamps): when set, the CTAs of r-block 0 record clock64() at the phase boundaries of
+// each role, 8 slots per tile: start, setup done, loads issued, first stage landed, MMAs issued, accumulators complete,
+// epilogue done, k-chunks.
+__device__ long long* g_i8_dbg = nullptr;
+
 // ---------------------------------------------------------------------------------------------------------------
 // grid = (r-blocks, tiles); the r-block index is fastest so the CTAs that share a tile's A slices run together.
 // tile_list[tile] = {pulsar, first compact column, columns (<= 64), k extent}; AS tile index = blockIdx.y (the host
@@ -165,6 +171,28 @@ gwb_synth_i8_kernel(double* __restrict__ G, int64_t g_ld, const int8_t* __restri
   const int64_t nkch = Jpad / I8_BK;
   const int64_t n_rblk = rcap / I8_BM;
 
+  long long* dbg = (g_i8_dbg != nullptr && blockIdx.x == 0) ? g_i8_dbg + size_t(blockIdx.y) * 8 : nullptr;
+  if (dbg && tid == 0) {
+    dbg[0] = clock64();
+    dbg[7] = nk;
+  }
+  auto load_stage = [&](int kc) {          // one elected thread: 6 Z-slice tiles + the stacked A-slice tile of k-chunk kc
+    const int st = kc % I8_STAGES;
+    unsigned char* sb = stage_base + size_t(st) * I8_STAGE_BYTES;
+    i8_mbar_expect_tx(full + st, I8_STAGE_BYTES);
+#pragma unroll
+    for (int s = 0; s < I8_SLICES; ++s) {
+      const int8_t* src = ZS + (((size_t(s) * P + p) * n_rblk + rblk) * nkch + kc) * I8_A_BYTES;
+      i8_bulk_load(sb + s * I8_A_BYTES, src, I8_A_BYTES, full + st);
+    }
+    const int8_t* srcb = AS + (size_t(blockIdx.y) * nkch + kc) * I8_B_BYTES;
+    i8_bulk_load(sb + I8_SLICES * I8_A_BYTES, srcb, I8_B_BYTES, full + st);
+  };
+  __shared__ double s_colscale[I8_BN];
+  if (tid >= 64 && tid < 64 + I8_BN) {       // scales of this tile's columns (read by the epilogue from shared memory)
+    const int n = tid - 64;
+    s_colscale[n] = (n < kcnt) ? colscale[kn0 + n] * zscale[p] : 0.0;
+  }
   if (tid == 0) {
     for (int s = 0; s < I8_STAGES; ++s) {
       i8_mbar_init(full + s, 1);
@@ -172,6 +200,9 @@ gwb_synth_i8_kernel(double* __restrict__ G, int64_t g_ld, const int8_t* __restri
     }
     i8_mbar_init(tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // the first ring of copies leaves before the TMEM allocation and the CTA-wide sync: their latency (~2.5k clk
+    // measured) overlaps the set-up
+    for (int kc = 0; kc < nk && kc < I8_STAGES; ++kc) load_stage(kc);
   }
   if (warp == 1) {  // one warp allocates the tensor memory; the address lands in shared memory
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(i8_smem_u32(tmem_addr_smem)),
@@ -182,108 +213,105 @@ gwb_synth_i8_kernel(double* __restrict__ G, int64_t g_ld, const int8_t* __restri
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_addr_smem;
+  if (dbg && tid == 0) dbg[1] = clock64();
 
-  if (warp == 0) {
-    // ---- producer: bulk-async copies of the operand tiles
-    if (lane == 0) {
-      for (int kc = 0; kc < nk; ++kc) {
-        const int st = kc % I8_STAGES;
-        const uint32_t ph = (kc / I8_STAGES) & 1;
-        i8_mbar_wait(empty + st, ph ^ 1);                 // the MMAs that read this stage have completed
-        unsigned char* sb = stage_base + size_t(st) * I8_STAGE_BYTES;
-        i8_mbar_expect_tx(full + st, I8_STAGE_BYTES);
-#pragma unroll
-        for (int s = 0; s < I8_SLICES; ++s) {
-          const int8_t* src = ZS + (((size_t(s) * P + p) * n_rblk + rblk) * nkch + kc) * I8_A_BYTES;
-          i8_bulk_load(sb + s * I8_A_BYTES, src, I8_A_BYTES, full + st);
-        }
-        const int8_t* srcb = AS + (size_t(blockIdx.y) * nkch + kc) * I8_B_BYTES;
-        i8_bulk_load(sb + I8_SLICES * I8_A_BYTES, srcb, I8_B_BYTES, full + st);
-      }
+  if (tid == 0) {
+    // ---- producer (warp 0, lane 0): the remaining k-chunks, each once the MMAs that read its stage have completed
+    for (int kc = I8_STAGES; kc < nk; ++kc) {
+      i8_mbar_wait(empty + kc % I8_STAGES, ((kc / I8_STAGES) & 1) ^ 1);
+      load_stage(kc);
     }
-  } else if (warp == 1) {
-    // ---- MMA issuer (one thread)
-    if (lane == 0) {
-      for (int kc = 0; kc < nk; ++kc) {
-        const int st = kc % I8_STAGES;
-        const uint32_t ph = (kc / I8_STAGES) & 1;
-        i8_mbar_wait(full + st, ph);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = i8_smem_u32(stage_base + size_t(st) * I8_STAGE_BYTES);
-        const uint32_t sbm = sa + I8_SLICES * I8_A_BYTES;
-        // stage layout of one operand: [row group][4 k-pieces of 16 B][8 rows][16 B]: lbo = 128, sbo = 512
+    if (dbg) dbg[2] = clock64();
+  } else if (tid == 32) {
+    // ---- MMA issuer (warp 1, lane 0)
+    for (int kc = 0; kc < nk; ++kc) {
+      const int st = kc % I8_STAGES;
+      const uint32_t ph = (kc / I8_STAGES) & 1;
+      i8_mbar_wait(full + st, ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (dbg && kc == 0) dbg[3] = clock64();
+      const uint32_t sa = i8_smem_u32(stage_base + size_t(st) * I8_STAGE_BYTES);
+      const uint32_t sbm = sa + I8_SLICES * I8_A_BYTES;
+      // stage layout of one operand: [row group][4 k-pieces of 16 B][8 rows][16 B]: lbo = 128, sbo = 512
 #pragma unroll
-        for (int kk = 0; kk < I8_BK / 32; ++kk) {          // one MMA consumes 32 bytes of K = two 16-byte pieces
-          const uint32_t first = (kc == 0 && kk == 0) ? 0u : 1u;
-          // (Z slice s, first A slice t0, A slices taken, opens): columns 64 (s + t0) .. ; N <= 256 per instruction; an
-          // instruction either overwrites all its columns (first k-step only) or accumulates into all of them, so the
-          // slice that first touches diagonal 6 (s = 1, t = 5) is issued on its own
-          constexpr int kPlan[10][4] = {{0, 0, 4, 1}, {0, 4, 2, 1}, {1, 0, 4, 0}, {1, 4, 1, 0}, {1, 5, 1, 1},
-                                        {2, 0, 4, 0}, {2, 4, 1, 0}, {3, 0, 4, 0}, {4, 0, 3, 0}, {5, 0, 2, 0}};
+      for (int kk = 0; kk < I8_BK / 32; ++kk) {          // one MMA consumes 32 bytes of K = two 16-byte pieces
+        const uint32_t first = (kc == 0 && kk == 0) ? 0u : 1u;
+        // (Z slice s, first A slice t0, A slices taken, opens): columns 64 (s + t0) .. ; N <= 256 per instruction; an
+        // instruction either overwrites all its columns (first k-step only) or accumulates into all of them, so the
+        // slice that first touches diagonal 6 (s = 1, t = 5) is issued on its own
+        constexpr int kPlan[10][4] = {{0, 0, 4, 1}, {0, 4, 2, 1}, {1, 0, 4, 0}, {1, 4, 1, 0}, {1, 5, 1, 1},
+                                      {2, 0, 4, 0}, {2, 4, 1, 0}, {3, 0, 4, 0}, {4, 0, 3, 0}, {5, 0, 2, 0}};
 #pragma unroll
-          for (int q = 0; q < 10; ++q) {
-            const int s = kPlan[q][0], t0 = kPlan[q][1], take = kPlan[q][2];
-            const uint64_t adesc = i8_smem_desc(sa + s * I8_A_BYTES + kk * 256, 128, 512);
-            const uint64_t bdesc = i8_smem_desc(sbm + t0 * (I8_BN * I8_BK) + kk * 256, 128, 512);
-            const uint32_t dcol = tmem_base + uint32_t((s + t0) * I8_BN);
-            i8_mma(dcol, adesc, bdesc, i8_instr_desc(take * I8_BN), kPlan[q][3] ? first : 1u);
-          }
+        for (int q = 0; q < 10; ++q) {
+          const int s = kPlan[q][0], t0 = kPlan[q][1], take = kPlan[q][2];
+          const uint64_t adesc = i8_smem_desc(sa + s * I8_A_BYTES + kk * 256, 128, 512);
+          const uint64_t bdesc = i8_smem_desc(sbm + t0 * (I8_BN * I8_BK) + kk * 256, 128, 512);
+          const uint32_t dcol = tmem_base + uint32_t((s + t0) * I8_BN);
+          i8_mma(dcol, adesc, bdesc, i8_instr_desc(take * I8_BN), kPlan[q][3] ? first : 1u);
         }
-        i8_umma_commit(empty + st);                        // frees the stage once these MMAs have read it
       }
-      i8_umma_commit(tmem_full);                           // accumulators complete
+      i8_umma_commit(empty + st);                        // frees the stage once these MMAs have read it
     }
-  } else {
-    // ---- epilogue: 4 warps, warp w owns TMEM lanes 32 (w % 4) .. +31 = realizations of this r-block
-    const int quarter = warp & 3;
+    i8_umma_commit(tmem_full);                           // accumulators complete
+    if (dbg) dbg[4] = clock64();
+  }
+
+  // ---- epilogue: all 8 warps.  Warp w reads TMEM lanes 32 (w % 4) .. +31 (= realizations of this r-block) and the
+  // knots 32 (w / 4) .. +31; the loads of diagonal d + 1 are in flight while diagonal d is folded in.
+  {
+    const int quarter = warp & 3, half = warp >> 2;
     const int64_t r = rblk * I8_BM + quarter * 32 + lane;
     i8_mbar_wait(tmem_full, 0);
+    __syncwarp();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const double zs = zscale[p];
-    for (int half = 0; half < 2; ++half) {                 // 32 knots at a time
-      double val[32];
+    if (dbg && tid == 64) dbg[5] = clock64();
+#define I8_TMEM_LD32(v, addr)                                                                                                 \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                     \
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                     \
+               "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                     \
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),   \
+                 "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),        \
+                 "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),       \
+                 "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                     \
+               : "r"(addr))
+    double val[32];
 #pragma unroll
-      for (int n = 0; n < 32; ++n) val[n] = 0.0;
-      if (nk > 0) {
-        double w = 1.0;
+    for (int n = 0; n < 32; ++n) val[n] = 0.0;
+    if (nk > 0) {
+      const uint32_t tbase = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(half * 32);
+      uint32_t va[32], vb[32];
+      I8_TMEM_LD32(va, tbase);
+      double w = 1.0;
 #pragma unroll
-        for (int d = 0; d < I8_DIAGS; ++d) {
-          uint32_t v[32];
-          const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(d * I8_BN + half * 32);
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-                "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-                "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-              : "r"(taddr));
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int n = 0; n < 32; ++n) {
-            // int32 -> double without the conversion pipe: 2^52 + 2^31 + x sits exactly in the mantissa of {0x43300000, x ^ 2^31}
-            const double x = __hiloint2double(0x43300000, static_cast<int>(v[n] ^ 0x80000000u)) - 4503601774854144.0;
-            val[n] = fma(x, w, val[n]);
-          }
-          w *= 0.00390625;                                 // 2^-8 per diagonal
+      for (int d = 0; d < I8_DIAGS; ++d) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (d + 1 < I8_DIAGS) {
+          if (d & 1) { I8_TMEM_LD32(va, tbase + uint32_t((d + 1) * I8_BN)); }
+          else       { I8_TMEM_LD32(vb, tbase + uint32_t((d + 1) * I8_BN)); }
         }
+#pragma unroll
+        for (int n = 0; n < 32; ++n) {
+          // int32 -> double without the conversion pipe: 2^52 + 2^31 + x sits exactly in the mantissa of {0x43300000, x ^ 2^31}
+          const uint32_t vi = (d & 1) ? vb[n] : va[n];
+          const double x = __hiloint2double(0x43300000, static_cast<int>(vi ^ 0x80000000u)) - 4503601774854144.0;
+          val[n] = fma(x, w, val[n]);
+        }
+        w *= 0.00390625;                                 // 2^-8 per diagonal
       }
-      if (r < nreal) {
-        // compact columns kn0 + n; pulsar blocks start at even columns and are padded to even length
-        const int kpad = (kcnt + 1) & ~1;
-        double* grow = G + size_t(r) * g_ld + kn0 + half * 32;
-        const double* cs = colscale + kn0 + half * 32;
+    }
+#undef I8_TMEM_LD32
+    if (r < nreal) {
+      // compact columns kn0 + n; pulsar blocks start at even columns and are padded to even length
+      const int kpad = (kcnt + 1) & ~1;
+      double* grow = G + size_t(r) * g_ld + kn0 + half * 32;
+      const double* cs = s_colscale + half * 32;
 #pragma unroll
-        for (int n = 0; n < 32; n += 2) {
-          if (half * 32 + n < kpad) {
-            const double s0 = cs[n] * zs, s1 = (half * 32 + n + 1 < kcnt) ? cs[n + 1] * zs : 0.0;
-            *reinterpret_cast<double2*>(grow + n) = make_double2(val[n] * s0, val[n + 1] * s1);
-          }
-        }
+      for (int n = 0; n < 32; n += 2) {
+        if (half * 32 + n < kpad) *reinterpret_cast<double2*>(grow + n) = make_double2(val[n] * cs[n], val[n + 1] * cs[n + 1]);
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    if (dbg && tid == 64) dbg[6] = clock64();
   }
   __syncthreads();
   if (warp == 1) {
