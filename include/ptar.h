@@ -98,10 +98,13 @@ typedef struct {
   /* per-pulsar red-noise statics */
   const double* rn_scale;    /* [n_psr][J] sqrt(prior)                                   */
   const double* rn_omega;    /* [n_psr][J/2] 2*pi*f_k                                    */
-  /* compact GWB grid for this batch of realizations: G[r][g_ld]; only the knots next to some TOA of a
-   * pulsar are present (ptar_gwb_synth) */
+  /* compact GWB grid for this batch of realizations, COLUMN-major: G[q][g_ldr], q < g_ld compact knot columns (only
+   * the knots next to some TOA of a pulsar are present, ptar_gwb_synth), row = realization of this call; g_ldr is a
+   * multiple of 4 >= nreal rounded up to 4.  The synthesis writes 32 consecutive realizations per store and the
+   * generator reads 4 consecutive realizations of a knot as one 32-byte sector. */
   const double* G;
   int64_t g_ld;
+  int64_t g_ldr;
   /* injected standard-normal draws (parity mode); all NULL => Philox */
   const double* z1;   /* [nreal][ld_out]                                                 */
   const double* z2;   /* [nreal][ld_out]                                                 */
@@ -175,7 +178,7 @@ int ptar_gwb_mix(double* Zm, const double* M, const double* zin, int n_psr, int 
  * even column and padded to even length with -1).  tile_list[n_tiles][4] = {pulsar, first column, columns
  * (<= 64), k extent} enumerates 64-column blocks, heaviest first; with lower_tri the k loop stops at the
  * tile's k extent (A[n][j] == 0 for j > n). */
-int ptar_gwb_synth(double* G, int64_t g_ld, const double* A, int64_t lda, const double* Zm, int J, int64_t nreal,
+int ptar_gwb_synth(double* G, int64_t g_ld, int64_t g_ldr, const double* A, int64_t lda, const double* Zm, int J, int64_t nreal,
                    const int32_t* tile_list, int n_tiles, const int32_t* knots, int lower_tri, void* stream);
 
 /* tcgen05 path of the synthesis (throughput mode; csrc/ptar_gwb_i8.cuh).  Both operands are fixed-point numbers with
@@ -183,7 +186,7 @@ int ptar_gwb_synth(double* G, int64_t g_ld, const double* A, int64_t lda, const 
  * ptar_gwb_slice_i8: Zm[p][r][J] (fp64) -> ZS, int8 digits in the tensor core's K-major core-matrix tile layout
  *   [slice][pulsar][rcap/128 r-blocks][Jpad/64 k-chunks][16][4][8][16]; zinv[p] = 2^48 / zscale[p]; rcap (multiple of 128)
  *   is the row capacity the buffer was laid out for (>= nreal), Jpad a multiple of 64 (>= J).
- * ptar_gwb_synth_i8: G[r][q] = sum_j A[knot(q)][j] Zm[p(q)][r][j] from the digit slices; AS holds the digits of the
+ * ptar_gwb_synth_i8: G[q][r] = sum_j A[knot(q)][j] Zm[p(q)][r][j] from the digit slices; AS holds the digits of the
  *   gathered rows of A tile by tile, in tile_list order: [tile][Jpad/64][slice][8][4][8][16]; colscale[q] = (scale of
  *   row knot(q) of A) * 2^-16; tile_list as in ptar_gwb_synth (64-column blocks; A lower triangular: k stops at the
  *    tile's k extent).  Exact int8 x int8 -> int32 products on tcgen05.mma.kind::i8; the slice pairs s + t <= 6 are kept
@@ -195,7 +198,7 @@ int ptar_gwb_mix_i8(int8_t* ZS, const double* M, const double* zinv, int n_psr, 
                     uint64_t seed, int64_t real0, void* stream);
 int ptar_gwb_slice_i8(int8_t* ZS, const double* Zm, const double* zinv, int n_psr, int J, int Jpad, int64_t nreal,
                       int64_t rcap, void* stream);
-int ptar_gwb_synth_i8(double* G, int64_t g_ld, const int8_t* AS, const double* colscale, const int8_t* ZS,
+int ptar_gwb_synth_i8(double* G, int64_t g_ld, int64_t g_ldr, const int8_t* AS, const double* colscale, const int8_t* ZS,
                       const double* zscale, int n_psr, int J, int Jpad, int64_t nreal, int64_t rcap,
                       const int32_t* tile_list, int n_tiles, void* stream);
 
@@ -235,7 +238,7 @@ typedef struct {
   int32_t n_syn_tiles;
   int32_t reserved;
   double* Zm;               /* scratch [n_psr][chunk][Jg]                                 */
-  double* Gbuf;             /* scratch [chunk][gen.g_ld]                                  */
+  double* Gbuf;             /* scratch [gen.g_ld][gen.g_ldr]                              */
   const double* gwb_zin;    /* parity mode: [nreal][n_psr][Jg] or NULL                    */
   /* tcgen05 synthesis (throughput mode only; all NULL / 0 selects the fp64 DMMA kernel) */
   const int8_t* AS;         /* digit slices of the gathered rows of A, tile_list_i8 order */

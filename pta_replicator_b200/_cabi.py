@@ -40,7 +40,7 @@ class GenParams(C.Structure):
         ("ep_ecorr", C.c_void_p), ("ep_bucket", C.c_void_p), ("ep_gidx", C.c_void_p), ("ep_gw", C.c_void_p),
         ("ep_ginv", C.c_void_p), ("psr_bucket_off", C.c_void_p), ("Ftile", C.c_void_p),
         ("rn_scale", C.c_void_p), ("rn_omega", C.c_void_p),
-        ("G", C.c_void_p), ("g_ld", C.c_int64),
+        ("G", C.c_void_p), ("g_ld", C.c_int64), ("g_ldr", C.c_int64),
         ("z1", C.c_void_p), ("z2", C.c_void_p), ("zb", C.c_void_p), ("zrn", C.c_void_p),
         ("n_bucket_total", C.c_int64),
         ("seed", C.c_uint64), ("real0", C.c_int64),
@@ -83,10 +83,10 @@ def lib():
     L.ptar_burst_delay.argtypes = [vp, vp, vp, C.c_double, C.c_double, C.c_double, C.c_double, i32, i64, vp]
     L.ptar_memory_delay.argtypes = [vp, vp, C.c_double, C.c_double, i32, i64, vp]
     L.ptar_gwb_mix.argtypes = [vp, vp, vp, i32, i32, i64, u64, i64, vp]
-    L.ptar_gwb_synth.argtypes = [vp, i64, vp, i64, vp, i32, i64, vp, i32, vp, i32, vp]
+    L.ptar_gwb_synth.argtypes = [vp, i64, i64, vp, i64, vp, i32, i64, vp, i32, vp, i32, vp]
     L.ptar_gwb_mix_i8.argtypes = [vp, vp, vp, i32, i32, i32, i64, i64, u64, i64, vp]
     L.ptar_gwb_slice_i8.argtypes = [vp, vp, vp, i32, i32, i32, i64, i64, vp]
-    L.ptar_gwb_synth_i8.argtypes = [vp, i64, vp, vp, vp, vp, i32, i32, i32, i64, i64, vp, i32, vp]
+    L.ptar_gwb_synth_i8.argtypes = [vp, i64, i64, vp, vp, vp, vp, i32, i32, i32, i64, i64, vp, i32, vp]
     L.ptar_debug_i8_timestamps.argtypes = [vp]
     L.ptar_generate.argtypes = [C.POINTER(GenParams), vp]
     L.ptar_generate_stage.argtypes = [C.POINTER(GenParams), i32, vp]

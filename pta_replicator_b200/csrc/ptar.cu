@@ -404,18 +404,19 @@ int ptar_gwb_mix_i8(int8_t* ZS, const double* M, const double* zinv, int n_psr, 
                                  "ptar_gwb_mix_i8");
 }
 
-int ptar_gwb_synth(double* G, int64_t g_ld, const double* A, int64_t lda, const double* Zm, int J, int64_t nreal,
+int ptar_gwb_synth(double* G, int64_t g_ld, int64_t g_ldr, const double* A, int64_t lda, const double* Zm, int J, int64_t nreal,
                    const int32_t* tile_list, int n_tiles, const int32_t* knots, int lower_tri, void* stream) {
   if (!G || !A || !Zm || !tile_list || !knots || J <= 0 || nreal <= 0 || n_tiles <= 0 || g_ld <= 0)
     return fail(-1, "ptar_gwb_synth: bad argument%s");
-  if ((J & 3) || (lda & 1) || lda < J || (g_ld & 1)) return fail(-2, "ptar_gwb_synth: need J %% 4 == 0, even lda >= J, even g_ld%s");
+  if ((J & 3) || (lda & 1) || lda < J || (g_ld & 1) || (g_ldr & 3) || g_ldr < nreal)
+    return fail(-2, "ptar_gwb_synth: need J %% 4 == 0, even lda >= J, even g_ld, g_ldr %% 4 == 0 >= nreal%s");
   const int64_t r_blocks = (nreal + ptar::DM_BC - 1) / ptar::DM_BC;
   if (r_blocks > 65535) return fail(-3, "ptar_gwb_synth: too many realizations per call%s");
   static SmemOptIn optin;
   if (int rc = opt_in_smem(ptar::gwb_synth_dmma_kernel, optin, ptar::DM_SMEM, "ptar_gwb_synth")) return rc;
   const dim3 grid(static_cast<unsigned>(n_tiles), static_cast<unsigned>(r_blocks));
   ptar::gwb_synth_dmma_kernel<<<grid, 256, ptar::DM_SMEM, static_cast<cudaStream_t>(stream)>>>(
-      G, g_ld, A, lda, Zm, J, nreal, tile_list, knots, lower_tri);
+      G, g_ld, g_ldr, A, lda, Zm, J, nreal, tile_list, knots, lower_tri);
   return check_launch("ptar_gwb_synth");
 }
 
@@ -430,13 +431,13 @@ int ptar_gwb_slice_i8(int8_t* ZS, const double* Zm, const double* zinv, int n_ps
   return check_launch("ptar_gwb_slice_i8");
 }
 
-int ptar_gwb_synth_i8(double* G, int64_t g_ld, const int8_t* AS, const double* colscale, const int8_t* ZS, const double* zscale,
+int ptar_gwb_synth_i8(double* G, int64_t g_ld, int64_t g_ldr, const int8_t* AS, const double* colscale, const int8_t* ZS, const double* zscale,
                       int n_psr, int J, int Jpad, int64_t nreal, int64_t rcap, const int32_t* tile_list, int n_tiles,
                       void* stream) {
   if (!G || !AS || !colscale || !ZS || !zscale || !tile_list || n_psr <= 0 || J <= 0 || nreal <= 0 || n_tiles <= 0 || g_ld <= 0)
     return fail(-1, "ptar_gwb_synth_i8: bad argument%s");
-  if (Jpad < J || (Jpad % ptar::I8_BK) || rcap < nreal || (rcap % ptar::I8_BM) || (g_ld & 1))
-    return fail(-2, "ptar_gwb_synth_i8: need Jpad %% 64 == 0 >= J, rcap %% 128 == 0 >= nreal, even g_ld%s");
+  if (Jpad < J || (Jpad % ptar::I8_BK) || rcap < nreal || (rcap % ptar::I8_BM) || (g_ld & 1) || (g_ldr & 3) || g_ldr < nreal)
+    return fail(-2, "ptar_gwb_synth_i8: need Jpad %% 64 == 0 >= J, rcap %% 128 == 0 >= nreal, even g_ld, g_ldr %% 4 == 0 >= nreal%s");
   if ((reinterpret_cast<uintptr_t>(AS) | reinterpret_cast<uintptr_t>(ZS)) & 15)
     return fail(-2, "ptar_gwb_synth_i8: AS / ZS must be 16-byte aligned%s");
   if (n_tiles > 65535) return fail(-3, "ptar_gwb_synth_i8: more than 65535 tiles%s");
@@ -444,7 +445,7 @@ int ptar_gwb_synth_i8(double* G, int64_t g_ld, const int8_t* AS, const double* c
   if (int rc = opt_in_smem(ptar::gwb_synth_i8_kernel, optin, ptar::I8_SMEM, "ptar_gwb_synth_i8")) return rc;
   const dim3 grid(static_cast<unsigned>((nreal + ptar::I8_BM - 1) / ptar::I8_BM), static_cast<unsigned>(n_tiles));
   ptar::gwb_synth_i8_kernel<<<grid, ptar::I8_THREADS, ptar::I8_SMEM, static_cast<cudaStream_t>(stream)>>>(
-      G, g_ld, AS, colscale, ZS, zscale, n_psr, J, Jpad, nreal, rcap, tile_list);
+      G, g_ld, g_ldr, AS, colscale, ZS, zscale, n_psr, J, Jpad, nreal, rcap, tile_list);
   return check_launch("ptar_gwb_synth_i8");
 }
 
@@ -468,6 +469,8 @@ int ptar_generate(const ptar_gen_params* pp, void* stream) {
   if ((p.flags & (PTAR_F_ECORR | PTAR_F_RED)) && (!p.eloc || !p.dtau)) return fail(-2, "ptar_generate: epoch terms need eloc/dtau%s");
   if ((p.flags & PTAR_F_GWB) && (!p.G || p.npts <= 1 || p.g_ld <= 0 || !p.ep_gidx || !p.ep_gw || !p.ep_ginv || !p.eloc || !p.dtau))
     return fail(-2, "ptar_generate: GWB needs G, g_ld, ep_gidx, ep_gw, ep_ginv, eloc, dtau%s");
+  if ((p.flags & PTAR_F_GWB) && ((p.g_ldr & 3) || p.g_ldr < ((p.nreal + 3) & ~3) || (reinterpret_cast<uintptr_t>(p.G) & 31)))
+    return fail(-2, "ptar_generate: G must be 32-byte aligned, column-major with g_ldr %% 4 == 0 >= nreal rounded up to 4%s");
   if ((p.flags & PTAR_F_DET) && !p.det) return fail(-2, "ptar_generate: DET needs det%s");
   const bool inject = p.z1 || p.z2 || p.zb || p.zrn;
   if (inject) {
@@ -547,10 +550,10 @@ int ptar_run_job(const ptar_job* job, int64_t real0, int32_t nreal, double* out,
     if (rc) return rc;
     if (i8) {   // tcgen05 path: exact int8 GEMMs on the digit slices, fp64 fix-up
       if (!job->colscale || !job->zscale || !job->tile_list_i8) return fail(-2, "ptar_run_job: tcgen05 GWB buffers missing%s");
-      rc = ptar_gwb_synth_i8(job->Gbuf, g.g_ld, job->AS, job->colscale, job->ZS, job->zscale, g.n_psr, job->Jg, job->Jpad, nreal,
+      rc = ptar_gwb_synth_i8(job->Gbuf, g.g_ld, g.g_ldr, job->AS, job->colscale, job->ZS, job->zscale, g.n_psr, job->Jg, job->Jpad, nreal,
                              job->rcap, job->tile_list_i8, job->n_syn_tiles, stream);
     } else {
-      rc = ptar_gwb_synth(job->Gbuf, g.g_ld, job->A, job->lda, job->Zm, job->Jg, nreal, job->tile_list, job->n_syn_tiles,
+      rc = ptar_gwb_synth(job->Gbuf, g.g_ld, g.g_ldr, job->A, job->lda, job->Zm, job->Jg, nreal, job->tile_list, job->n_syn_tiles,
                           job->knots, job->lower_tri, stream);
     }
     if (rc) return rc;

@@ -274,16 +274,19 @@ __device__ __forceinline__ void gen_body(const ptar_gen_params& P, const PhiloxK
       const int e = idx / RG, rg = idx % RG;
       const int ge = tile.ep_start + e;
       double add0[4] = {0.0, 0.0, 0.0, 0.0}, add1[4] = {0.0, 0.0, 0.0, 0.0};
-      if (has_gwb) {
+      if (has_gwb && rg * 4 < nr) {
+        // column-major grid: the 4 realizations of this group at knot j (and j + 1) are one 32-byte sector each
         const int j = P.ep_gidx[ge];
         const double gwt = P.ep_gw[ge], ginv = P.ep_ginv[ge];
+        const double2* Gc = reinterpret_cast<const double2*>(P.G + size_t(j) * P.g_ldr + r0 + rg * 4);
+        const double2* Gn = reinterpret_cast<const double2*>(P.G + size_t(j + 1) * P.g_ldr + r0 + rg * 4);
+        const double2 a01 = __ldg(Gc), a23 = __ldg(Gc + 1), b01 = __ldg(Gn), b23 = __ldg(Gn + 1);
+        const double g0[4] = {a01.x, a01.y, a23.x, a23.y}, g1[4] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
         for (int l = 0; l < 4; ++l) {
-          const int r = rg * 4 + l;
-          if (r < nr) {
-            const double* Gr = P.G + size_t(r0 + r) * P.g_ld + j;
-            const double g0 = __ldg(Gr), dg = __ldg(Gr + 1) - g0;
-            add0[l] = fma(gwt, dg, g0);
+          if (rg * 4 + l < nr) {
+            const double dg = g1[l] - g0[l];
+            add0[l] = fma(gwt, dg, g0[l]);
             add1[l] = dg * ginv;
           }
         }
@@ -494,12 +497,15 @@ __global__ void __launch_bounds__(EPK_THREADS, 2) epoch_kernel(const ptar_gen_pa
       if (idx < tile.n_ep * RG) {
         const int e = idx / RG, rg = idx % RG;
         const int j = P.ep_gidx[tile.ep_start + e];
+        if (rg * 4 < nr) {
+          const double2* Gc = reinterpret_cast<const double2*>(P.G + size_t(j) * P.g_ldr + r0 + rg * 4);
+          const double2* Gn = reinterpret_cast<const double2*>(P.G + size_t(j + 1) * P.g_ldr + r0 + rg * 4);
+          const double2 a01 = __ldg(Gc), a23 = __ldg(Gc + 1), b01 = __ldg(Gn), b23 = __ldg(Gn + 1);
+          g0[m][0] = a01.x; g0[m][1] = a01.y; g0[m][2] = a23.x; g0[m][3] = a23.y;
+          g1[m][0] = b01.x; g1[m][1] = b01.y; g1[m][2] = b23.x; g1[m][3] = b23.y;
+        } else {
 #pragma unroll
-        for (int l = 0; l < 4; ++l) {
-          const int r = rg * 4 + l;
-          const double* Gr = P.G + size_t(r0 + (r < nr ? r : 0)) * P.g_ld + j;
-          g0[m][l] = __ldg(Gr);
-          g1[m][l] = __ldg(Gr + 1);
+          for (int l = 0; l < 4; ++l) g0[m][l] = g1[m][l] = 0.0;
         }
       }
     }

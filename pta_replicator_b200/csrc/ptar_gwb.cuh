@@ -182,7 +182,7 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool va
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(bytes) : "memory");
 }
 
-__global__ void __launch_bounds__(256, 2) gwb_synth_dmma_kernel(double* __restrict__ G, int64_t g_ld,
+__global__ void __launch_bounds__(256, 2) gwb_synth_dmma_kernel(double* __restrict__ G, int64_t g_ld, int64_t g_ldr,
                                                                  const double* __restrict__ A, int64_t lda,
                                                                  const double* __restrict__ Z, int J, int64_t nreal,
                                                                  const int32_t* __restrict__ tile_list,
@@ -259,8 +259,8 @@ __global__ void __launch_bounds__(256, 2) gwb_synth_dmma_kernel(double* __restri
     }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
-  // the compact grid shares its column index with knots[]: G[r][kn0 + n]; pulsar blocks start at even
-  // columns and are padded to even length (pad knots = -1 -> zero rows), so pairs are 16-byte aligned
+  // the compact grid shares its column index with knots[] and is column-major: G[kn0 + n][r]; pulsar blocks are padded
+  // to even length (pad knots = -1 -> zero rows)
   const int kpad = (kcnt + 1) & ~1;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -269,8 +269,10 @@ __global__ void __launch_bounds__(256, 2) gwb_synth_dmma_kernel(double* __restri
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
       const int n = wn + m * 8 + 2 * fk;
-      if (n < kpad)
-        *reinterpret_cast<double2*>(G + size_t(r) * g_ld + kn0 + n) = make_double2(acc[i][m][0], acc[i][m][1]);
+      if (n < kpad) {
+        G[size_t(kn0 + n) * g_ldr + r] = acc[i][m][0];
+        G[size_t(kn0 + n + 1) * g_ldr + r] = acc[i][m][1];
+      }
     }
   }
 }

@@ -152,7 +152,7 @@ __device__ long long* g_i8_dbg = nullptr;
 // tile_list[tile] = {pulsar, first compact column, columns (<= 64), k extent}; AS tile index = blockIdx.y (the host
 // builds AS in tile_list order).  colscale[q] = sA[knot(q)] * 2^-16; zscale[p] = sZ[p].
 __global__ void __launch_bounds__(I8_THREADS, 1)
-gwb_synth_i8_kernel(double* __restrict__ G, int64_t g_ld, const int8_t* __restrict__ AS, const double* __restrict__ colscale,
+gwb_synth_i8_kernel(double* __restrict__ G, int64_t g_ld, int64_t g_ldr, const int8_t* __restrict__ AS, const double* __restrict__ colscale,
                     const int8_t* __restrict__ ZS, const double* __restrict__ zscale, int P, int J, int Jpad, int64_t nreal,
                     int64_t rcap, const int32_t* __restrict__ tile_list) {
   extern __shared__ __align__(128) unsigned char i8_smem[];
@@ -293,21 +293,30 @@ gwb_synth_i8_kernel(double* __restrict__ G, int64_t g_ld, const int8_t* __restri
         for (int n = 0; n < 32; ++n) {
           // int32 -> double without the conversion pipe: 2^52 + 2^31 + x sits exactly in the mantissa of {0x43300000, x ^ 2^31}
           const uint32_t vi = (d & 1) ? vb[n] : va[n];
+#ifdef I8_EPI_NOMATH
+          val[n] = __hiloint2double(0x43300000, static_cast<int>(vi));
+#else
           const double x = __hiloint2double(0x43300000, static_cast<int>(vi ^ 0x80000000u)) - 4503601774854144.0;
           val[n] = fma(x, w, val[n]);
+#endif
         }
         w *= 0.00390625;                                 // 2^-8 per diagonal
       }
     }
 #undef I8_TMEM_LD32
+#ifdef I8_EPI_NOSTORE
+    if (r < nreal && val[5] == 1.2345e-300) {
+#else
     if (r < nreal) {
-      // compact columns kn0 + n; pulsar blocks start at even columns and are padded to even length
+#endif
+      // column-major grid G[kn0 + n][r]: the 32 lanes of a warp are 32 consecutive realizations -> one 256-byte store per
+      // knot (row-major stores of a thread's 32 knots were 16 bytes per 32-byte sector: 5.9k of the 8.4k epilogue clocks)
       const int kpad = (kcnt + 1) & ~1;
-      double* grow = G + size_t(r) * g_ld + kn0 + half * 32;
+      double* gcol = G + size_t(kn0 + half * 32) * g_ldr + r;
       const double* cs = s_colscale + half * 32;
 #pragma unroll
-      for (int n = 0; n < 32; n += 2) {
-        if (half * 32 + n < kpad) *reinterpret_cast<double2*>(grow + n) = make_double2(val[n] * cs[n], val[n + 1] * cs[n + 1]);
+      for (int n = 0; n < 32; ++n) {
+        if (half * 32 + n < kpad) gcol[size_t(n) * g_ldr] = val[n] * cs[n];
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -30,15 +30,17 @@ def _both_syntheses(b, R, seed=5, real0=8):
     job, keep = b._job(st, R, seed, None, 0)
     stream = _cabi.current_stream()
     _cabi.check(L.ptar_gwb_mix(job.Zm, job.M, None, b.n_psr, job.Jg, R, seed, real0, stream), "mix")
-    Gd = torch.zeros(R * st["g_ld"], dtype=torch.float64, device=b.device)
-    Gi = torch.full((R * st["g_ld"],), float("nan"), dtype=torch.float64, device=b.device)
-    _cabi.check(L.ptar_gwb_synth(Gd.data_ptr(), st["g_ld"], job.A, job.lda, job.Zm, job.Jg, R, job.tile_list, job.n_syn_tiles,
+    ldr = job.gen.g_ldr
+    Gd = torch.zeros(ldr * st["g_ld"], dtype=torch.float64, device=b.device)
+    Gi = torch.full((ldr * st["g_ld"],), float("nan"), dtype=torch.float64, device=b.device)
+    _cabi.check(L.ptar_gwb_synth(Gd.data_ptr(), st["g_ld"], ldr, job.A, job.lda, job.Zm, job.Jg, R, job.tile_list, job.n_syn_tiles,
                                  job.knots, job.lower_tri, stream), "synth")
     _cabi.check(L.ptar_gwb_slice_i8(job.ZS, job.Zm, job.zinv, b.n_psr, job.Jg, job.Jpad, R, job.rcap, stream), "slice")
-    _cabi.check(L.ptar_gwb_synth_i8(Gi.data_ptr(), st["g_ld"], job.AS, job.colscale, job.ZS, job.zscale, b.n_psr, job.Jg, job.Jpad,
+    _cabi.check(L.ptar_gwb_synth_i8(Gi.data_ptr(), st["g_ld"], ldr, job.AS, job.colscale, job.ZS, job.zscale, b.n_psr, job.Jg, job.Jpad,
                                     R, job.rcap, job.tile_list_i8, job.n_syn_tiles, stream), "synth_i8")
     torch.cuda.synchronize()
-    return Gd.view(R, -1), Gi.view(R, -1), job, keep, st
+    # the grid is column-major [g_ld][g_ldr]: return [R, g_ld] views
+    return Gd.view(-1, ldr)[:, :R].T, Gi.view(-1, ldr)[:, :R].T, job, keep, st
 
 
 @pytest.mark.parametrize("npsr,R", [(3, 40), (5, 200), (67, 256)])
