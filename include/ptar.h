@@ -134,11 +134,12 @@ const char* ptar_last_error(void);
  * part zeroed).  info[b] = 0, or k>0 if the leading minor of order k is not PD.  n <= 1024. */
 int ptar_cholesky_lower(double* L, const double* A, int n, int batch, int* info, void* stream);
 
-/* F[row][2k], F[row][2k+1] = trig(2*pi * tprime[row] * freqs[psr(row)][k]) in the reference's
- * operation order; convention 0 -> (sin, cos), 1 -> (cos, sin).  out index:
- * out[row_off[row] + col*col_stride] so the caller chooses row-major or per-tile layouts. */
+/* F[row][2k], F[row][2k+1] = trig(2*pi * tprime[row] * freqs[psr(row)][k] (+ phase[psr(row)][k])) in the reference's
+ * operation order; convention 0 -> (sin, cos), 1 -> (cos, sin); phase = NULL or the `pshift` random phases
+ * (red_noise.py:83-84).  out index: out[row_off[row] + col*col_stride] so the caller chooses row-major or per-tile
+ * layouts. */
 int ptar_fourier_basis(double* out, const int64_t* row_off, int64_t col_stride,
-                       const double* tprime, const int32_t* row_psr, const double* freqs,
+                       const double* tprime, const int32_t* row_psr, const double* freqs, const double* phase,
                        int K, int convention, int64_t nrows, void* stream);
 
 /* Continuous-wave delay per TOA.  src[16] and psr_par[n_psr][4] = {fplus, fcross, cosMu, pd_sec}

@@ -304,6 +304,62 @@ def make_f4(ref):
     np.savez(os.path.join(GOLD, "ref_f4.npz"), **store)
 
 
+def make_fourier(ref):
+    """create_fourier_design_matrix_red with the options the injection path never uses: pshift (random phases from the
+    global stream), logf / fmin / fmax, Tspan (red_noise.py:61-101)."""
+    rng = np.random.default_rng(31)
+    t = np.sort(rng.uniform(53000, 58800, 120)) * 86400.0
+    out = {"t": t}
+    np.random.seed(4242)
+    out["F_pshift"], out["f_pshift"] = ref.red_noise.create_fourier_design_matrix_red(t, nmodes=20, pshift=True)
+    np.random.seed(4243)
+    out["F_pshift_ls"], _ = ref.red_noise.create_fourier_design_matrix_red(t, nmodes=20, pshift=True, libstempo_convention=True)
+    out["F_logf"], out["f_logf"] = ref.red_noise.create_fourier_design_matrix_red(t, nmodes=20, logf=True, fmin=2e-9, fmax=3e-7)
+    out["F_lin"], out["f_lin"] = ref.red_noise.create_fourier_design_matrix_red(t, nmodes=20, fmin=2e-9, fmax=3e-7)
+    out["F_tspan"], out["f_tspan"] = ref.red_noise.create_fourier_design_matrix_red(t, nmodes=20, Tspan=6.0e8)
+    np.savez(os.path.join(GOLD, "ref_fourier.npz"), **out)
+
+
+def make_real(ref):
+    """The reference's real NANOGrav 15-yr files (test_partim: B1855+09, B1937+21, J1909-3744; unsorted TOAs, 7.8k / 23k /
+    35k TOAs, ELONG/ELAT positions, -f backend flags): the columns the hot path reads, stored compactly (the tim files
+    are 26 MB of text), the bucket counts of the unmodified ``quantize_fast`` and every 40th TOA of the unmodified
+    white / ECORR / red-noise injections with the 15-yr noise dictionary."""
+    from pta_replicator_b200 import noise_dict as nd
+    out = {}
+    names = ["B1855+09", "B1937+21", "J1909-3744"]
+    noise = nd.load_noise_dict()
+    psrs = []
+    for i, name in enumerate(names):
+        par = partim.read_par(os.path.join(REF, "test_partim", "par", name + ".par"))
+        c = partim.read_tim(os.path.join(REF, "test_partim", "tim", name + ".tim"))
+        fl = np.array([f.get("f", "") for f in c["flags"]])
+        be, inv = np.unique(fl, return_inverse=True)
+        mjd = np.asarray(c["mjd"], dtype=np.longdouble)
+        hi = mjd.astype(np.float64)
+        out[f"name_{i}"] = np.array(name)
+        out[f"elong_elat_{i}"] = np.array([par["_loc"]["ELONG"], par["_loc"]["ELAT"]])
+        out[f"mjd_hi_{i}"], out[f"mjd_lo_{i}"] = hi, (mjd - hi.astype(np.longdouble)).astype(np.float64)
+        out[f"err_us_{i}"] = np.asarray(c["err_us"], np.float64)
+        out[f"flag_idx_{i}"], out[f"backends_{i}"] = inv.astype(np.uint8), be
+        psrs.append(refstubs.StubPulsar(name, par["_loc"], mjd, c["err_us"], c["flags"]))
+        for tag, width in (("1s", 1.0 / 86400.0), ("0p1d", 0.1)):
+            ave, U = ref.white_noise.quantize_fast(np.asarray(mjd, dtype=float), dt=width)
+            out[f"nbucket_{tag}_{i}"] = np.array(U.shape[1])
+        pp = nd.per_pulsar(noise, name)
+        pbe = np.array(pp["backends"])
+        out[f"dict_backends_{i}"] = pbe
+        p = psrs[-1]
+        ref.white_noise.add_measurement_noise(p, efac=np.asarray(pp["efac"]), log10_equad=np.asarray(pp["log10_equad"]), flagid="f",
+                                              flags=pbe, seed=10660 + i)
+        ref.white_noise.add_jitter(p, log10_ecorr=np.asarray(pp["log10_ecorr"]), flagid="f", flags=pbe, coarsegrain=1.0 / 86400.0,
+                                   seed=17763 + i)
+        ref.red_noise.add_red_noise(p, pp["rn_log10_A"], pp["rn_gamma"], components=30, seed=19870 + i)
+        for sig in ("measurement_noise", "jitter", "red_noise"):
+            out[f"{sig}_{i}"] = p.signal_seconds(f"{p.name}_{sig}")[::40]
+    np.savez_compressed(os.path.join(GOLD, "ref_real3.npz"), **out)
+
+
 def make_orf(ref):
     rng = np.random.default_rng(3)
     n = 9
@@ -330,6 +386,8 @@ def main():
     make_small(ref)
     make_flags(ref)
     make_orf(ref)
+    make_fourier(ref)
+    make_real(ref)
     make_catalog(ref)
     make_f4(ref)
     make_outliers(ref)

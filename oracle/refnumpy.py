@@ -90,21 +90,28 @@ def ecorr_per_bucket(values, flags, toa_flags, firsts):
 
 
 # --------------------------------------------------------------------------- red noise
-def fourier_basis(t_sec, nmodes=30, Tspan=None, libstempo_convention=False, modes=None):
-    """red_noise.py:61-101 (no ``pshift``, linear spacing).  Returns ``(F[N,2K], Ffreqs[2K])``."""
+def fourier_basis(t_sec, nmodes=30, Tspan=None, libstempo_convention=False, modes=None, logf=False, fmin=None, fmax=None,
+                  ranphase=None):
+    """red_noise.py:61-101.  ``ranphase`` = the ``pshift`` phases (the reference draws them with
+    ``np.random.uniform(0, 2 pi, nmodes)`` at :83; pass that array).  Returns ``(F[N,2K], Ffreqs[2K])``."""
     t = np.asarray(t_sec, dtype=float)
     T = Tspan if Tspan is not None else t.max() - t.min()
     if modes is not None:
         f = np.asarray(modes, dtype=float)
-    else:
+    elif fmin is None and fmax is None and not logf:
         f = 1.0 * np.arange(1, nmodes + 1) / T
+    else:
+        fmin = 1 / T if fmin is None else fmin
+        fmax = nmodes / T if fmax is None else fmax
+        f = np.logspace(np.log10(fmin), np.log10(fmax), nmodes) if logf else np.linspace(fmin, fmax, nmodes)
+    ph = np.zeros(len(f)) if ranphase is None else np.asarray(ranphase, dtype=float)
     F = np.zeros((len(t), 2 * len(f)))
     if libstempo_convention:
-        arg = 2 * np.pi * (t[:, None] - t[0, None]) * f[None, :]
+        arg = 2 * np.pi * (t[:, None] - t[0, None]) * f[None, :] + ph[None, :]
         F[:, 0::2] = np.cos(arg)
         F[:, 1::2] = np.sin(arg)
     else:
-        arg = 2 * np.pi * t[:, None] * f[None, :]
+        arg = 2 * np.pi * t[:, None] * f[None, :] + ph[None, :]
         F[:, 0::2] = np.sin(arg)
         F[:, 1::2] = np.cos(arg)
     return F, np.repeat(f, 2)

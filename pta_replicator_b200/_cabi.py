@@ -77,7 +77,7 @@ def lib():
     L.ptar_version.restype = C.c_int
     L.ptar_last_error.restype = C.c_char_p
     L.ptar_cholesky_lower.argtypes = [vp, vp, i32, i32, vp, vp]
-    L.ptar_fourier_basis.argtypes = [vp, vp, i64, vp, vp, vp, i32, i32, i64, vp]
+    L.ptar_fourier_basis.argtypes = [vp, vp, i64, vp, vp, vp, vp, i32, i32, i64, vp]
     L.ptar_cgw_delay.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i64, vp]
     L.ptar_cw_catalog.argtypes = [vp, vp, i64, C.POINTER(C.c_double), vp, i64, C.c_double, C.c_double, i32, i32, i32, i32, vp, vp, i32, vp]
     L.ptar_burst_delay.argtypes = [vp, vp, vp, C.c_double, C.c_double, C.c_double, C.c_double, i32, i64, vp]

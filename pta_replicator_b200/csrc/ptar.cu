@@ -54,14 +54,15 @@ int check_launch(const char* what) {
 // red_noise.py:92-101 -- operation order kept: (2*pi * t) * f, then sin / cos.
 __global__ void fourier_basis_kernel(double* __restrict__ out, const int64_t* __restrict__ row_off,
                                      int64_t col_stride, const double* __restrict__ tprime,
-                                     const int32_t* __restrict__ row_psr, const double* __restrict__ freqs, int K,
-                                     int convention, int64_t nrows) {
+                                     const int32_t* __restrict__ row_psr, const double* __restrict__ freqs,
+                                     const double* __restrict__ phase, int K, int convention, int64_t nrows) {
   const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= nrows * K) return;
   const int64_t row = idx / K;
   const int k = static_cast<int>(idx % K);
   const double f = freqs[size_t(row_psr[row]) * K + k];
-  const double arg = __dmul_rn(__dmul_rn(6.283185307179586, tprime[row]), f);
+  double arg = __dmul_rn(__dmul_rn(6.283185307179586, tprime[row]), f);
+  if (phase) arg = __dadd_rn(arg, phase[size_t(row_psr[row]) * K + k]);   // pshift (red_noise.py:83-84)
   double s, c;
   sincos(arg, &s, &c);
   double* o = out + row_off[row];
@@ -328,14 +329,14 @@ int ptar_cholesky_lower(double* L, const double* A, int n, int batch, int* info,
 }
 
 int ptar_fourier_basis(double* out, const int64_t* row_off, int64_t col_stride, const double* tprime,
-                       const int32_t* row_psr, const double* freqs, int K, int convention, int64_t nrows,
-                       void* stream) {
+                       const int32_t* row_psr, const double* freqs, const double* phase, int K, int convention,
+                       int64_t nrows, void* stream) {
   if (!out || !row_off || !tprime || !row_psr || !freqs || K <= 0 || nrows < 0)
     return fail(-1, "ptar_fourier_basis: bad argument%s");
   if (nrows == 0) return 0;
   const int64_t total = nrows * K;
   fourier_basis_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      out, row_off, col_stride, tprime, row_psr, freqs, K, convention, nrows);
+      out, row_off, col_stride, tprime, row_psr, freqs, phase, K, convention, nrows);
   return check_launch("ptar_fourier_basis");
 }
 

@@ -47,8 +47,8 @@ def create_fourier_design_matrix_red(toas: np.ndarray, nmodes: int = 30, Tspan: 
         fmin = 1 / T if fmin is None else fmin
         fmax = nmodes / T if fmax is None else fmax
         f = np.logspace(np.log10(fmin), np.log10(fmax), nmodes) if logf else np.linspace(fmin, fmax, nmodes)
-    if pshift:
-        raise NotImplementedError("pshift is never enabled on the injection path (red_noise.py:83-84, :125)")
+    # random phase per mode from the global legacy stream, exactly where the reference draws it (red_noise.py:83-84)
+    ranphase = np.random.uniform(0.0, 2 * np.pi, nmodes) if pshift else None
     N = len(toas)
     tp = toas - toas[0] if libstempo_convention else toas
     F = torch.empty((N, 2 * nmodes), dtype=torch.float64, device=dev)
@@ -56,8 +56,9 @@ def create_fourier_design_matrix_red(toas: np.ndarray, nmodes: int = 30, Tspan: 
     tp_d = torch.from_numpy(np.ascontiguousarray(tp)).to(dev)
     psr_d = torch.zeros(N, dtype=torch.int32, device=dev)
     f_d = torch.from_numpy(np.ascontiguousarray(f, dtype=np.float64)).to(dev)
+    ph_d = None if ranphase is None else torch.from_numpy(np.ascontiguousarray(ranphase, dtype=np.float64)).to(dev)
     _cabi.check(_cabi.lib().ptar_fourier_basis(F.data_ptr(), off.data_ptr(), 1, tp_d.data_ptr(), psr_d.data_ptr(),
-                                               f_d.data_ptr(), nmodes, int(bool(libstempo_convention)), N,
+                                               f_d.data_ptr(), _cabi.ptr(ph_d), nmodes, int(bool(libstempo_convention)), N,
                                                _cabi.current_stream()), "ptar_fourier_basis")
     out = F.cpu().numpy()   # synchronises; the temporaries above stay referenced until here
     return out, np.repeat(f, 2)

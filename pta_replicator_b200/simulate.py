@@ -156,8 +156,15 @@ class SimulatedPulsar:
     def __repr__(self):
         return f"SimulatedPulsar({self.name})"
 
+    def _is_pint(self):
+        return not isinstance(self.toas, TOAs)
+
     def update_residuals(self):
-        self.residuals = Residuals(self.toas, self.model)
+        if self._is_pint():     # PINT-backed pulsar (pint_bridge.load_pulsar_pint): simulate.py:40-42
+            from pint.residuals import Residuals as PintResiduals
+            self.residuals = PintResiduals(self.toas, self.model)
+        else:
+            self.residuals = Residuals(self.toas, self.model)
 
     def update_added_signals(self, signal_name, param_dict, dt=None):
         # simulate.py:83-89: ledgers are None until make_ideal(); names are unique
@@ -170,13 +177,27 @@ class SimulatedPulsar:
             self.added_signals_time[signal_name] = dt
 
     def fit(self, fitter="auto", **fitter_kwargs):
-        raise NotImplementedError("timing-model fitting needs PINT; out of scope for the B200 hot path")
+        """Refit the timing model (simulate.py:44-69): delegated to PINT for PINT-backed pulsars."""
+        from . import pint_bridge
+        if not self._is_pint():
+            raise pint_bridge.PintUnavailable("fit() needs a PINT timing model: load the pulsar with pint_bridge.load_pulsar_pint")
+        pint_bridge.fit(self, fitter, **fitter_kwargs)
 
     def to_enterprise(self, ephem="DE440"):
-        raise NotImplementedError("enterprise export needs PINT + enterprise; out of scope for the B200 hot path")
+        """enterprise ``Pulsar`` (simulate.py:91-95): delegated to enterprise for PINT-backed pulsars."""
+        from . import pint_bridge
+        if not self._is_pint():
+            raise pint_bridge.PintUnavailable("to_enterprise() needs PINT TOAs and a PINT model: load the pulsar with "
+                                              "pint_bridge.load_pulsar_pint")
+        return pint_bridge.to_enterprise(self, ephem)
 
     def write_partim(self, outpar: str, outtim: str, tempo2: bool = False):
-        """Write the current (signal-shifted) TOAs; the par file is copied through."""
+        """Write the current (signal-shifted) TOAs and the par file (simulate.py:71-77).  PINT-backed pulsars go through
+        PINT's writers; the PINT-free container writes Tempo2 ``FORMAT 1`` lines itself (MJD with 19 decimals, all flags;
+        ``partim.read_tim`` reads them back exactly) and copies the par file through."""
+        if self._is_pint():
+            from . import pint_bridge
+            return pint_bridge.write_partim(self, outpar, outtim, tempo2)
         cols = {"name": self.toas.names, "freq": self.toas.freq, "mjd": self.toas.table["tdbld"],
                 "err_us": self.toas.err_us, "site": self.toas.site, "flags": self.toas.table["flags"]}
         partim.write_tim(outtim, cols)

@@ -290,4 +290,5 @@ def test_fullsize_taylor_epochs_against_exact_epochs_on_the_same_draws(ng15, tol
     for i in range(b.n_psr):
         sl = slice(b.toa_off[i], b.toa_off[i] + b.ntoa[i])
         worst = max(worst, ((got[:, sl] - ref[:, sl]).abs().max() / ref[:, sl].std()).item())
+    print(f"Taylor epochs vs exact epochs, rn_taylor_tol = {tol:g}: max|d|/rms = {worst:.3e}")
     assert worst < TAYLOR, worst
