@@ -383,7 +383,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip other_configs / config5 blocks")
     ap.add_argument("--bare", action="store_true", help="headline measurement only (used for the library-variant sub-runs)")
     ap.add_argument("--split", action="store_true", help="epoch kernel + TOA kernel (two launches) instead of the fused generator")
-    ap.add_argument("--taylor-tol", type=float, default=1e-14,
+    ap.add_argument("--taylor-tol", type=float, default=1e-13,
                     help="PulsarBatch(rn_taylor_tol=...): remainder bound of the in-epoch Taylor step, relative to the red-noise rms")
     ap.add_argument("--c5-nreal", type=int, default=100000)
     ap.add_argument("--c5-chunk", type=int, default=512)
@@ -492,7 +492,7 @@ def main():
                      "one merged N(0, w1^2 + w2^2) draw per TOA (same Gaussian law)")
         var["two_white_draws" if not args.two_draws else "merged_white_draw"] = v
         del b1
-        for name, lib in (("box_muller_fp32_accurate", ge.LIB_BM1), ("box_muller_fp64", ge.LIB_BM2)):
+        for name, lib in (("box_muller_fp32_accurate", ge.LIB_BM1), ("box_muller_fp64", ge.LIB_BM2), ("philox4x32_7_rounds", ge.LIB_PHILOX7)):
             if os.path.isfile(lib) and not os.environ.get("PTAR_B200_LIB"):
                 var[name] = bm_variant(lib, args)
         line["variants"] = var

@@ -57,6 +57,112 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// ---- pieces of the epoch stage shared by the fused kernel (gen_body) and the standalone epoch kernel: one copy of
+// the arithmetic, so the two schedules agree bit for bit by construction.
+
+// Red-noise coefficients a = sqrt(prior) * z of RB realizations and their first two time derivatives (1/2 folded into
+// the 2nd): As = [3][J][RB].  One work item = one (even, odd) column pair x 4 realizations (red_noise.py:126-127).
+template <int RB, bool INJECT, int NTHREADS>
+__device__ __forceinline__ void rn_coefficients(const ptar_gen_params& P, const PhiloxKeys& K, uint32_t psr, int J, int r0,
+                                                int nr, uint64_t rgroup0, double* As, int tid) {
+  constexpr int RG = RB / 4;
+  const double* scale = P.rn_scale + size_t(psr) * J;
+  const double* om = P.rn_omega + size_t(psr) * (J / 2);
+  const double sgn_even = P.rn_convention ? 1.0 : -1.0;
+  double* A0 = As;
+  double* A1 = As + size_t(J) * RB;
+  double* A2 = As + size_t(2) * J * RB;
+  for (int idx = tid; idx < (J / 2) * RG; idx += NTHREADS) {
+    const int k = idx / RG, rg = idx % RG;
+    const int je = 2 * k, jo = 2 * k + 1;
+    double ye[4], yo[4];
+    if (INJECT) {
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        const int r = rg * 4 + l;
+        const bool ok = r < nr;
+        const size_t zi = (size_t(r0 + (ok ? r : 0)) * P.n_psr + psr) * J;
+        ye[l] = ok ? P.zrn[zi + je] : 0.0;
+        yo[l] = ok ? P.zrn[zi + jo] : 0.0;
+      }
+    } else {
+      float n[4];
+      normals4(n, je, PTAR_K_RED, psr, rgroup0 + rg, K);
+#pragma unroll
+      for (int l = 0; l < 4; ++l) ye[l] = static_cast<double>(n[l]);
+      normals4(n, jo, PTAR_K_RED, psr, rgroup0 + rg, K);
+#pragma unroll
+      for (int l = 0; l < 4; ++l) yo[l] = static_cast<double>(n[l]);
+    }
+    const double se = scale[je], so = scale[jo], w = om[k];
+    const double h = -0.5 * w * w;
+    double ae[4], ao[4];
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      ae[l] = se * ye[l];
+      ao[l] = so * yo[l];
+    }
+    auto put = [&](double* row, double v0, double v1, double v2, double v3) {
+      double2* q = reinterpret_cast<double2*>(row + rg * 4);
+      q[0] = make_double2(v0, v1);
+      q[1] = make_double2(v2, v3);
+    };
+    put(A0 + je * RB, ae[0], ae[1], ae[2], ae[3]);
+    put(A0 + jo * RB, ao[0], ao[1], ao[2], ao[3]);
+    const double s1 = sgn_even * w, s2 = -sgn_even * w;
+    put(A1 + je * RB, s1 * ao[0], s1 * ao[1], s1 * ao[2], s1 * ao[3]);
+    put(A1 + jo * RB, s2 * ae[0], s2 * ae[1], s2 * ae[2], s2 * ae[3]);
+    put(A2 + je * RB, h * ae[0], h * ae[1], h * ae[2], h * ae[3]);
+    put(A2 + jo * RB, h * ao[0], h * ao[1], h * ao[2], h * ao[3]);
+  }
+}
+
+// GWB grid values of 4 consecutive realizations (first local row rl) at knot column j and j + 1: the grid is
+// column-major, so each is one 32-byte sector.
+__device__ __forceinline__ void load_grid4(const ptar_gen_params& P, int j, int r_first, double g0[4], double g1[4]) {
+  const double2* Gc = reinterpret_cast<const double2*>(P.G + size_t(j) * P.g_ldr + r_first);
+  const double2* Gn = reinterpret_cast<const double2*>(P.G + size_t(j + 1) * P.g_ldr + r_first);
+  const double2 a01 = __ldg(Gc), a23 = __ldg(Gc + 1), b01 = __ldg(Gn), b23 = __ldg(Gn + 1);
+  g0[0] = a01.x; g0[1] = a01.y; g0[2] = a23.x; g0[3] = a23.y;
+  g1[0] = b01.x; g1[1] = b01.y; g1[2] = b23.x; g1[3] = b23.y;
+}
+
+// Additive terms of one (epoch, 4 realizations): GWB interpolation at the epoch reference time and its slope
+// (red_noise.py:286-287; exactly linear inside an epoch), plus the ECORR draw of the epoch's bucket (white_noise.py:182).
+// nv = how many of the 4 realizations exist; r_first = row of the first one in the injected arrays.
+template <bool INJECT>
+__device__ __forceinline__ void epoch_addends4(const ptar_gen_params& P, const PhiloxKeys& K, int ge, uint32_t psr, uint64_t rfield,
+                                               int r_first, int nv, bool has_gwb, bool has_ecorr, const double g0[4],
+                                               const double g1[4], double add0[4], double add1[4]) {
+#pragma unroll
+  for (int l = 0; l < 4; ++l) add0[l] = add1[l] = 0.0;
+  if (has_gwb) {
+    const double gwt = P.ep_gw[ge], ginv = P.ep_ginv[ge];
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      if (l < nv) {
+        const double dg = g1[l] - g0[l];
+        add0[l] = fma(gwt, dg, g0[l]);
+        add1[l] = dg * ginv;
+      }
+    }
+  }
+  if (has_ecorr) {
+    const double ec = P.ep_ecorr[ge];
+    if (INJECT) {
+      const size_t zo = P.psr_bucket_off[psr] + P.ep_bucket[ge];
+#pragma unroll
+      for (int l = 0; l < 4; ++l)
+        if (l < nv) add0[l] += ec * P.zb[size_t(r_first + l) * P.n_bucket_total + zo];
+    } else {
+      float n[4];
+      normals4(n, P.ep_bucket[ge], PTAR_K_ECORR, psr, rfield, K);
+#pragma unroll
+      for (int l = 0; l < 4; ++l) add0[l] += ec * static_cast<double>(n[l]);
+    }
+  }
+}
+
 // WHITE / DET: -1 = decided at run time from P.flags (generic build, used by the parity mode);
 // WHITE 0/1/2 = no white noise / one merged draw / two draws, DET 0/1 = no / with deterministic term
 // (specialised builds of the throughput mode: the flag tests disappear from the inner loop).
@@ -154,53 +260,8 @@ __device__ __forceinline__ void gen_body(const ptar_gen_params& P, const PhiloxK
           "l"(src), "r"(bytes), "r"(smem_u32(mbar))
           : "memory");
     }
-    // coefficients a = sqrt(prior) * z for RC realizations and their first two time derivatives
-    // (1/2 folded into the 2nd); one work item = one (cos, sin) column pair x 4 realizations.
-    // Overlaps the bulk copy.
-    {
-      const double* scale = P.rn_scale + size_t(psr) * J;
-      const double* om = P.rn_omega + size_t(psr) * (J / 2);
-      const double sgn_even = P.rn_convention ? 1.0 : -1.0;
-      double* A0 = As;
-      double* A1 = As + size_t(J) * RC;
-      double* A2 = As + size_t(2) * J * RC;
-      for (int idx = tid; idx < (J / 2) * RG; idx += GEN_THREADS) {
-        const int k = idx / RG, rg = idx % RG;
-        const int je = 2 * k, jo = 2 * k + 1;
-        double ye[4], yo[4];
-        if (INJECT) {
-#pragma unroll
-          for (int l = 0; l < 4; ++l) {
-            const int r = rg * 4 + l;
-            const bool ok = r < nr;
-            const size_t zi = (size_t(r0 + (ok ? r : 0)) * P.n_psr + psr) * J;
-            ye[l] = ok ? P.zrn[zi + je] : 0.0;
-            yo[l] = ok ? P.zrn[zi + jo] : 0.0;
-          }
-        } else {
-          float n[4];
-          normals4(n, je, PTAR_K_RED, psr, rgroup0 + rg, K);
-#pragma unroll
-          for (int l = 0; l < 4; ++l) ye[l] = static_cast<double>(n[l]);
-          normals4(n, jo, PTAR_K_RED, psr, rgroup0 + rg, K);
-#pragma unroll
-          for (int l = 0; l < 4; ++l) yo[l] = static_cast<double>(n[l]);
-        }
-        const double se = scale[je], so = scale[jo], w = om[k];
-        const double h = -0.5 * w * w;
-#pragma unroll
-        for (int l = 0; l < 4; ++l) {
-          const int c = rg * 4 + l;
-          const double a_e = se * ye[l], a_o = so * yo[l];
-          A0[je * RC + c] = a_e;
-          A0[jo * RC + c] = a_o;
-          A1[je * RC + c] = sgn_even * w * a_o;
-          A1[jo * RC + c] = -sgn_even * w * a_e;
-          A2[je * RC + c] = h * a_e;
-          A2[jo * RC + c] = h * a_o;
-        }
-      }
-    }
+    // coefficients and their first two time derivatives: overlaps the bulk copy
+    rn_coefficients<RC, INJECT, GEN_THREADS>(P, K, psr, J, r0, nr, rgroup0, As, tid);
     __syncthreads();
     {  // wait for the basis tile
       uint32_t done = 0;
@@ -273,38 +334,10 @@ __device__ __forceinline__ void gen_body(const ptar_gen_params& P, const PhiloxK
     for (int idx = tid; idx < tile.n_ep * RG; idx += GEN_THREADS) {
       const int e = idx / RG, rg = idx % RG;
       const int ge = tile.ep_start + e;
-      double add0[4] = {0.0, 0.0, 0.0, 0.0}, add1[4] = {0.0, 0.0, 0.0, 0.0};
-      if (has_gwb && rg * 4 < nr) {
-        // column-major grid: the 4 realizations of this group at knot j (and j + 1) are one 32-byte sector each
-        const int j = P.ep_gidx[ge];
-        const double gwt = P.ep_gw[ge], ginv = P.ep_ginv[ge];
-        const double2* Gc = reinterpret_cast<const double2*>(P.G + size_t(j) * P.g_ldr + r0 + rg * 4);
-        const double2* Gn = reinterpret_cast<const double2*>(P.G + size_t(j + 1) * P.g_ldr + r0 + rg * 4);
-        const double2 a01 = __ldg(Gc), a23 = __ldg(Gc + 1), b01 = __ldg(Gn), b23 = __ldg(Gn + 1);
-        const double g0[4] = {a01.x, a01.y, a23.x, a23.y}, g1[4] = {b01.x, b01.y, b23.x, b23.y};
-#pragma unroll
-        for (int l = 0; l < 4; ++l) {
-          if (rg * 4 + l < nr) {
-            const double dg = g1[l] - g0[l];
-            add0[l] = fma(gwt, dg, g0[l]);
-            add1[l] = dg * ginv;
-          }
-        }
-      }
-      if (has_ecorr) {
-        const double ec = P.ep_ecorr[ge];
-        if (INJECT) {
-          const size_t zo = P.psr_bucket_off[psr] + P.ep_bucket[ge];
-#pragma unroll
-          for (int l = 0; l < 4; ++l)
-            if (rg * 4 + l < nr) add0[l] += ec * P.zb[size_t(r0 + rg * 4 + l) * P.n_bucket_total + zo];
-        } else {
-          float n[4];
-          normals4(n, P.ep_bucket[ge], PTAR_K_ECORR, psr, rgroup0 + rg, K);
-#pragma unroll
-          for (int l = 0; l < 4; ++l) add0[l] += ec * static_cast<double>(n[l]);
-        }
-      }
+      double g0[4] = {0.0, 0.0, 0.0, 0.0}, g1[4] = {0.0, 0.0, 0.0, 0.0}, add0[4], add1[4];
+      const int nv = nr - rg * 4;                       // realizations of this group that exist (may be <= 0)
+      if (has_gwb && nv > 0) load_grid4(P, P.ep_gidx[ge], r0 + rg * 4, g0, g1);
+      epoch_addends4<INJECT>(P, K, ge, psr, rgroup0 + rg, r0 + rg * 4, nv, has_gwb, has_ecorr, g0, g1, add0, add1);
 #pragma unroll
       for (int l = 0; l < 4; ++l) {
         double* c = Cs + e * CSS + (rg * 4 + l) * 3;
@@ -490,24 +523,14 @@ __global__ void __launch_bounds__(EPK_THREADS, 2) epoch_kernel(const ptar_gen_pa
   // thread.  The scattered grid loads are issued here and consumed after the coefficient generation below.
   constexpr int ADD_ITEMS = EP * RG / EPK_THREADS;  // 2
   double g0[ADD_ITEMS][4], g1[ADD_ITEMS][4];
-  if (has_gwb) {
 #pragma unroll
-    for (int m = 0; m < ADD_ITEMS; ++m) {
-      const int idx = tid + m * EPK_THREADS;
-      if (idx < tile.n_ep * RG) {
-        const int e = idx / RG, rg = idx % RG;
-        const int j = P.ep_gidx[tile.ep_start + e];
-        if (rg * 4 < nr) {
-          const double2* Gc = reinterpret_cast<const double2*>(P.G + size_t(j) * P.g_ldr + r0 + rg * 4);
-          const double2* Gn = reinterpret_cast<const double2*>(P.G + size_t(j + 1) * P.g_ldr + r0 + rg * 4);
-          const double2 a01 = __ldg(Gc), a23 = __ldg(Gc + 1), b01 = __ldg(Gn), b23 = __ldg(Gn + 1);
-          g0[m][0] = a01.x; g0[m][1] = a01.y; g0[m][2] = a23.x; g0[m][3] = a23.y;
-          g1[m][0] = b01.x; g1[m][1] = b01.y; g1[m][2] = b23.x; g1[m][3] = b23.y;
-        } else {
+  for (int m = 0; m < ADD_ITEMS; ++m) {
 #pragma unroll
-          for (int l = 0; l < 4; ++l) g0[m][l] = g1[m][l] = 0.0;
-        }
-      }
+    for (int l = 0; l < 4; ++l) g0[m][l] = g1[m][l] = 0.0;
+    const int idx = tid + m * EPK_THREADS;
+    if (has_gwb && idx < tile.n_ep * RG) {
+      const int e = idx / RG, rg = idx % RG;
+      if (rg * 4 < nr) load_grid4(P, P.ep_gidx[tile.ep_start + e], r0 + rg * 4, g0[m], g1[m]);
     }
   }
   auto finish_add = [&]() {
@@ -516,33 +539,9 @@ __global__ void __launch_bounds__(EPK_THREADS, 2) epoch_kernel(const ptar_gen_pa
       const int idx = tid + m * EPK_THREADS;
       if (idx < tile.n_ep * RG) {
         const int e = idx / RG, rg = idx % RG;
-        const int ge = tile.ep_start + e;
-        double add0[4] = {0.0, 0.0, 0.0, 0.0}, add1[4] = {0.0, 0.0, 0.0, 0.0};
-        if (has_gwb) {
-          const double gwt = P.ep_gw[ge], ginv = P.ep_ginv[ge];
-#pragma unroll
-          for (int l = 0; l < 4; ++l) {
-            if (rg * 4 + l < nr) {
-              const double dg = g1[m][l] - g0[m][l];
-              add0[l] = fma(gwt, dg, g0[m][l]);
-              add1[l] = dg * ginv;
-            }
-          }
-        }
-        if (has_ecorr) {
-          const double ec = P.ep_ecorr[ge];
-          if (INJECT) {
-            const size_t zo = P.psr_bucket_off[psr] + P.ep_bucket[ge];
-#pragma unroll
-            for (int l = 0; l < 4; ++l)
-              if (rg * 4 + l < nr) add0[l] += ec * P.zb[size_t(r0 + rg * 4 + l) * P.n_bucket_total + zo];
-          } else {
-            float n[4];
-            normals4(n, P.ep_bucket[ge], PTAR_K_ECORR, psr, rgroup0 + rg, K);
-#pragma unroll
-            for (int l = 0; l < 4; ++l) add0[l] += ec * static_cast<double>(n[l]);
-          }
-        }
+        double add0[4], add1[4];
+        epoch_addends4<INJECT>(P, K, tile.ep_start + e, psr, rgroup0 + rg, r0 + rg * 4, nr - rg * 4, has_gwb, has_ecorr, g0[m],
+                               g1[m], add0, add1);
         double2* q = reinterpret_cast<double2*>(Add + (size_t(e) * RB + rg * 4) * 2);
 #pragma unroll
         for (int l = 0; l < 4; ++l) q[l] = make_double2(add0[l], add1[l]);
@@ -563,57 +562,8 @@ __global__ void __launch_bounds__(EPK_THREADS, 2) epoch_kernel(const ptar_gen_pa
     for (int l = 0; l < 2; ++l) acc[i][l][0] = acc[i][l][1] = acc[i][l][2] = 0.0;
 
   if (has_red) {
-    {  // coefficients and their first two time derivatives for 32 realizations (overlaps the bulk copy)
-      const double* scale = P.rn_scale + size_t(psr) * J;
-      const double* om = P.rn_omega + size_t(psr) * (J / 2);
-      const double sgn_even = P.rn_convention ? 1.0 : -1.0;
-      double* A0 = As;
-      double* A1 = As + size_t(J) * RB;
-      double* A2 = As + size_t(2) * J * RB;
-      for (int idx = tid; idx < (J / 2) * RG; idx += EPK_THREADS) {
-        const int k = idx / RG, rg = idx % RG;
-        const int je = 2 * k, jo = 2 * k + 1;
-        double ye[4], yo[4];
-        if (INJECT) {
-#pragma unroll
-          for (int l = 0; l < 4; ++l) {
-            const int r = rg * 4 + l;
-            const bool ok = r < nr;
-            const size_t zi = (size_t(r0 + (ok ? r : 0)) * P.n_psr + psr) * J;
-            ye[l] = ok ? P.zrn[zi + je] : 0.0;
-            yo[l] = ok ? P.zrn[zi + jo] : 0.0;
-          }
-        } else {
-          float n[4];
-          normals4(n, je, PTAR_K_RED, psr, rgroup0 + rg, K);
-#pragma unroll
-          for (int l = 0; l < 4; ++l) ye[l] = static_cast<double>(n[l]);
-          normals4(n, jo, PTAR_K_RED, psr, rgroup0 + rg, K);
-#pragma unroll
-          for (int l = 0; l < 4; ++l) yo[l] = static_cast<double>(n[l]);
-        }
-        const double se = scale[je], so = scale[jo], w = om[k];
-        const double h = -0.5 * w * w;
-        double ae[4], ao[4];
-#pragma unroll
-        for (int l = 0; l < 4; ++l) {
-          ae[l] = se * ye[l];
-          ao[l] = so * yo[l];
-        }
-        auto put = [&](double* row, double v0, double v1, double v2, double v3) {
-          double2* q = reinterpret_cast<double2*>(row + rg * 4);
-          q[0] = make_double2(v0, v1);
-          q[1] = make_double2(v2, v3);
-        };
-        put(A0 + je * RB, ae[0], ae[1], ae[2], ae[3]);
-        put(A0 + jo * RB, ao[0], ao[1], ao[2], ao[3]);
-        const double s1 = sgn_even * w, s2 = -sgn_even * w;
-        put(A1 + je * RB, s1 * ao[0], s1 * ao[1], s1 * ao[2], s1 * ao[3]);
-        put(A1 + jo * RB, s2 * ae[0], s2 * ae[1], s2 * ae[2], s2 * ae[3]);
-        put(A2 + je * RB, h * ae[0], h * ae[1], h * ae[2], h * ae[3]);
-        put(A2 + jo * RB, h * ao[0], h * ao[1], h * ao[2], h * ao[3]);
-      }
-    }
+    // coefficients and their first two time derivatives for 32 realizations (overlaps the bulk copy)
+    rn_coefficients<RB, INJECT, EPK_THREADS>(P, K, psr, J, r0, nr, rgroup0, As, tid);
     if (has_add) finish_add();
     __syncthreads();  // As (and Add, and thread 0's mbarrier init) visible
     {
