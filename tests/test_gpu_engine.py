@@ -71,10 +71,11 @@ def test_injected_draws_all_signals_epoch_mode(exact):
     import torch
     _, spec = load_flags_case()
     psrs = _psrs(spec)
-    b = _batch(psrs, spec, exact_epochs=exact)
+    b = _batch(psrs, spec, exact_epochs=exact, rn_taylor_tol=1e-14)       # 1e-14 forces the 3-term Taylor step (nd = 3)
     st = b.compile()
     if not exact:
         assert st["n_epochs"] < 0.3 * b.n_toa_total and int(st["tiles_host"][:, 6].max()) == 3
+        assert int(_batch(psrs, spec).compile()["tiles_host"][:, 6].max()) == 2    # the default tolerance (1e-13): 2 terms
     R, P = 6, len(spec)
     rng = np.random.default_rng(5)
     Jg = st["gwb_T_Jreal"]
