@@ -2,7 +2,12 @@
 """Turn an `ncu --set full --import-source on` report into the markdown / json summaries kept under
 profiles/ (run where ncu is installed; no GPU needed):
 
-    python tools/summarize_ncu.py gpurun_out/prof_gen.ncu-rep profiles/r01_gen_kernel --traffic-key gen_kernel
+    python tools/summarize_ncu.py gpurun_out/prof.ncu-rep profiles/r02_kernels --traffic-key gen_kernel \
+        --real-per-launch 1000 --traffic-out profiles/r02_traffic.json
+
+Every kernel in the report gets a metric table, its SASS opcode mix and warp-state samples; the traffic json
+(dram bytes per launch of the --traffic-key kernel) is stamped with the hash of the kernel sources it was captured from
+(bench.py compares it with the build it runs and marks `roofline.traffic` stale otherwise).
 """
 import collections
 import csv
@@ -22,12 +27,29 @@ KEYS = [
     "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__pipe_shared_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_tensor_subpipe_imma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed",
 ]
 
 
-def ncu_csv(rep, page):
-    out = subprocess.run(["ncu", "-i", rep, "--page", page, "--csv"], capture_output=True, text=True).stdout
+def ncu_csv(rep, page, kernel=None):
+    cmd = ["ncu", "-i", rep, "--page", page, "--csv"] + (["--kernel-name", "regex:" + kernel] if kernel else [])
+    out = subprocess.run(cmd, capture_output=True, text=True).stdout
     return list(csv.reader(io.StringIO(out)))
+
+
+def source_hash():
+    import hashlib
+    import os
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pta_replicator_b200", "csrc")
+    h = hashlib.sha256()
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            with open(os.path.join(d, f), "rb") as fh:
+                h.update(fh.read())
+    return h.hexdigest()[:16]
 
 
 def to_bytes(v, unit):
@@ -68,36 +90,57 @@ def main():
             traffic[f"{tkey}_grid"] = d["launch__grid_size"][0]
             if rpl:
                 traffic[f"{tkey}_realizations_per_launch"] = rpl
-    src = ncu_csv(rep, "source")
-    hi = [i for i, r in enumerate(src) if r and r[0] == "Address"]
-    if hi:
+    seen = set()
+    for r in raw[2:]:
+        name = dict(zip(hdr, r))["Kernel Name"]
+        short = name.split("(")[0].split("<")[0].split("::")[-1].split()[-1]
+        if short in seen:
+            continue
+        seen.add(short)
+        src = ncu_csv(rep, "source", short)
+        hi = [i for i, r2 in enumerate(src) if r2 and r2[0] == "Address"]
+        if not hi:
+            continue
         h = src[hi[0]]
         data = src[hi[0] + 1:(hi[1] - 1 if len(hi) > 1 else len(src))]
         ix = {n: i for i, n in enumerate(h)}
         op, ops = collections.Counter(), collections.Counter()
         tot_i = tot_s = 0
-        for r in data:
-            if len(r) <= ix["# Samples"]:
+        for r2 in data:
+            if len(r2) <= ix["# Samples"]:
                 continue
-            toks = r[ix["Source"]].strip().split()
+            toks = r2[ix["Source"]].strip().split()
             if not toks:
                 continue
             o = (toks[1] if toks[0].startswith("@") and len(toks) > 1 else toks[0]).split(".")[0]
-            ni, ns = int(r[ix["Instructions Executed"]] or 0), int(r[ix["# Samples"]] or 0)
+            try:
+                ni, ns = int(r2[ix["Instructions Executed"]] or 0), int(r2[ix["# Samples"]] or 0)
+            except ValueError:
+                continue
             op[o] += ni; ops[o] += ns; tot_i += ni; tot_s += ns
-        md.append("### SASS opcode mix (first kernel; warp instructions executed, share of stall samples)\n")
+        md.append(f"### `{short}`: SASS opcode mix (warp instructions executed, share of stall samples)\n")
         md.append("| opcode | executed | % instr | % samples |\n|---|---|---|---|")
         for o, c in op.most_common(22):
             md.append(f"| {o} | {c} | {100 * c / max(tot_i, 1):.1f} | {100 * ops[o] / max(tot_s, 1):.1f} |")
         st = [n for n in h if n.startswith("stall_") and "Not Issued" not in n]
-        tot = {n: sum(int(r[ix[n]] or 0) for r in data if len(r) > ix[n]) for n in st}
-        md.append("\n### warp-state samples\n")
-        md.append(", ".join(f"{k[6:]} {100 * v / max(tot_s, 1):.1f}%" for k, v in sorted(tot.items(), key=lambda kv: -kv[1])[:10]))
-        marks = [o for o in op if o in ("UBLKCP", "UTMALDG", "DMMA", "LDGSTS", "SYNCS", "UTCHMMA")]
-        md.append("\nBlackwell/Hopper-class instructions present: " + (", ".join(f"{m} x{op[m]}" for m in marks) or "none"))
+        tot = {}
+        for n in st:
+            t = 0
+            for r2 in data:
+                if len(r2) > ix[n]:
+                    try:
+                        t += int(r2[ix[n]] or 0)
+                    except ValueError:
+                        pass
+            tot[n] = t
+        md.append("\nwarp-state samples: " + ", ".join(f"{k[6:]} {100 * v / max(tot_s, 1):.1f}%" for k, v in sorted(tot.items(), key=lambda kv: -kv[1])[:10]))
+        marks = [o for o in op if o in ("UBLKCP", "UTMALDG", "DMMA", "LDGSTS", "SYNCS", "UTCHMMA", "UTCIMMA", "LDTM", "UTCBAR")]
+        md.append("\nBlackwell/Hopper-class instructions executed: " + (", ".join(f"{m} x{op[m]}" for m in marks) or "none") + "\n")
     open(stem + ".md", "w").write("\n".join(md) + "\n")
     if traffic:
-        open(stem.rsplit("/", 1)[0] + "/r01_traffic.json", "w").write(json.dumps(traffic, indent=1) + "\n")
+        traffic["source_hash"] = source_hash()
+        tout = sys.argv[sys.argv.index("--traffic-out") + 1] if "--traffic-out" in sys.argv else stem + "_traffic.json"
+        open(tout, "w").write(json.dumps(traffic, indent=1) + "\n")
     print("wrote", stem + ".md")
 
 
