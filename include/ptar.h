@@ -185,11 +185,11 @@ int ptar_gwb_synth(double* G, int64_t g_ld, int64_t g_ldr, const double* A, int6
 /* tcgen05 path of the synthesis (throughput mode; csrc/ptar_gwb_i8.cuh).  Both operands are fixed-point numbers with
  * PTAR_I8_SLICES signed radix-256 digits: value = scale * sum_s digit_s 2^(-8(s+1)), |value / scale| <= 1/4.
  * ptar_gwb_slice_i8: Zm[p][r][J] (fp64) -> ZS, int8 digits in the tensor core's K-major core-matrix tile layout
- *   [slice][pulsar][rcap/128 r-blocks][Jpad/64 k-chunks][16][4][8][16]; zinv[p] = 2^48 / zscale[p]; rcap (multiple of 128)
- *   is the row capacity the buffer was laid out for (>= nreal), Jpad a multiple of 64 (>= J).
+ *   [slice][pulsar][rcap/128 r-blocks][Jpad/32 k-chunks][16][2][8][16]; zinv[p] = 2^48 / zscale[p]; rcap (multiple of 128)
+ *   is the row capacity the buffer was laid out for (>= nreal), Jpad a multiple of 32 (>= J).
  * ptar_gwb_synth_i8: G[q][r] = sum_j A[knot(q)][j] Zm[p(q)][r][j] from the digit slices; AS holds the digits of the
- *   gathered rows of A tile by tile, in tile_list order: [tile][Jpad/64][slice][8][4][8][16]; colscale[q] = (scale of
- *   row knot(q) of A) * 2^-16; tile_list as in ptar_gwb_synth (64-column blocks; A lower triangular: k stops at the
+ *   gathered rows of A tile by tile, in tile_list order: [tile][Jpad/32][slice][4][2][8][16]; colscale[q] = (scale of
+ *   row knot(q) of A) * 2^-16; tile_list as in ptar_gwb_synth but with 32-column blocks ( A lower triangular: k stops at the
  *    tile's k extent).  Exact int8 x int8 -> int32 products on tcgen05.mma.kind::i8; the slice pairs s + t <= 6 are kept
  *   (dropped weight <= 2^-56 of full scale), the result is rounded once per output in fp64.
  * ptar_gwb_mix_i8: ptar_gwb_mix (Philox draws) with the slicing fused into its epilogue: ZS directly, no fp64 Zm
@@ -247,10 +247,10 @@ typedef struct {
   int8_t* ZS;               /* scratch: digit slices of Zm, PTAR_I8_SLICES*n_psr*rcap*Jpad bytes */
   const double* zscale;     /* [n_psr]                                                    */
   const double* zinv;       /* [n_psr] 2^48 / zscale                                      */
-  const int32_t* tile_list_i8; /* [n_syn_tiles][4], pulsar-major                          */
+  const int32_t* tile_list_i8; /* [n_syn_tiles_i8][4]: 32-column blocks, pulsar-major     */
   int64_t rcap;             /* row capacity of ZS (multiple of 128, >= chunk)             */
-  int32_t Jpad;             /* multiple of 64, >= Jg                                      */
-  int32_t reserved2;
+  int32_t Jpad;             /* multiple of 32, >= Jg                                      */
+  int32_t n_syn_tiles_i8;
 } ptar_job;
 
 int ptar_run_job(const ptar_job* job, int64_t real0, int32_t nreal, double* out, void* stream);

@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("PTAR_B200_LIB") or os.path.join(_HERE, "csrc", "libpt
 TILE_TOAS = 1024
 TILE_EPOCHS = 64
 TOA_ALIGN = 4
-I8_SLICES, I8_BM, I8_BN, I8_BK = 6, 128, 64, 64   # tcgen05 GWB synthesis tile (csrc/ptar_gwb_i8.cuh)
+I8_SLICES, I8_BM, I8_BN, I8_BK = 6, 128, 32, 32   # tcgen05 GWB synthesis tile (csrc/ptar_gwb_i8.cuh)
 
 F_WHITE, F_ECORR, F_RED, F_GWB, F_DET, F_WHITE1 = 1, 2, 4, 8, 16, 32
 K_WHITE1, K_WHITE2, K_ECORR, K_RED, K_GWB = 1, 2, 3, 4, 5
@@ -54,7 +54,7 @@ class Job(C.Structure):
                 ("lower_tri", C.c_int32), ("tile_list", C.c_void_p), ("knots", C.c_void_p), ("n_syn_tiles", C.c_int32),
                 ("reserved", C.c_int32), ("Zm", C.c_void_p), ("Gbuf", C.c_void_p), ("gwb_zin", C.c_void_p),
                 ("AS", C.c_void_p), ("colscale", C.c_void_p), ("ZS", C.c_void_p), ("zscale", C.c_void_p), ("zinv", C.c_void_p),
-                ("tile_list_i8", C.c_void_p), ("rcap", C.c_int64), ("Jpad", C.c_int32), ("reserved2", C.c_int32)]
+                ("tile_list_i8", C.c_void_p), ("rcap", C.c_int64), ("Jpad", C.c_int32), ("n_syn_tiles_i8", C.c_int32)]
 
 
 _lib = None

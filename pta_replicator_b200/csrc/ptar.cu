@@ -400,7 +400,7 @@ int ptar_gwb_mix_i8(int8_t* ZS, const double* M, const double* zinv, int n_psr, 
   if (n_psr > 8 * ptar::MX_MAXNT) return fail(-3, "ptar_gwb_mix_i8: more than 72 pulsars (use ptar_gwb_mix + ptar_gwb_slice_i8)%s");
   if (real0 & 3) return fail(-2, "ptar_gwb_mix_i8: real0 must be a multiple of 4%s");
   if (Jpad < J || (Jpad % ptar::I8_BK) || rcap < nreal || (rcap % ptar::I8_BM))
-    return fail(-2, "ptar_gwb_mix_i8: need Jpad %% 64 == 0 >= J and rcap %% 128 == 0 >= nreal%s");
+    return fail(-2, "ptar_gwb_mix_i8: need Jpad %% 32 == 0 >= J and rcap %% 128 == 0 >= nreal%s");
   return launch_mix<false, true>(nullptr, M, nullptr, n_psr, J, nreal, seed, real0, ZS, zinv, Jpad, rcap, static_cast<cudaStream_t>(stream),
                                  "ptar_gwb_mix_i8");
 }
@@ -425,7 +425,7 @@ int ptar_gwb_slice_i8(int8_t* ZS, const double* Zm, const double* zinv, int n_ps
                       void* stream) {
   if (!ZS || !Zm || !zinv || n_psr <= 0 || J <= 0 || nreal <= 0) return fail(-1, "ptar_gwb_slice_i8: bad argument%s");
   if (Jpad < J || (Jpad % ptar::I8_BK) || rcap < nreal || (rcap % ptar::I8_BM))
-    return fail(-2, "ptar_gwb_slice_i8: need Jpad %% 64 == 0 >= J and rcap %% 128 == 0 >= nreal%s");
+    return fail(-2, "ptar_gwb_slice_i8: need Jpad %% 32 == 0 >= J and rcap %% 128 == 0 >= nreal%s");
   const int64_t total = ((nreal + 7) / 8) * (Jpad / 16) * 8 * n_psr;
   ptar::gwb_slice_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       ZS, Zm, zinv, n_psr, J, Jpad, nreal, rcap);
@@ -438,7 +438,7 @@ int ptar_gwb_synth_i8(double* G, int64_t g_ld, int64_t g_ldr, const int8_t* AS, 
   if (!G || !AS || !colscale || !ZS || !zscale || !tile_list || n_psr <= 0 || J <= 0 || nreal <= 0 || n_tiles <= 0 || g_ld <= 0)
     return fail(-1, "ptar_gwb_synth_i8: bad argument%s");
   if (Jpad < J || (Jpad % ptar::I8_BK) || rcap < nreal || (rcap % ptar::I8_BM) || (g_ld & 1) || (g_ldr & 3) || g_ldr < nreal)
-    return fail(-2, "ptar_gwb_synth_i8: need Jpad %% 64 == 0 >= J, rcap %% 128 == 0 >= nreal, even g_ld, g_ldr %% 4 == 0 >= nreal%s");
+    return fail(-2, "ptar_gwb_synth_i8: need Jpad %% 32 == 0 >= J, rcap %% 128 == 0 >= nreal, even g_ld, g_ldr %% 4 == 0 >= nreal%s");
   if ((reinterpret_cast<uintptr_t>(AS) | reinterpret_cast<uintptr_t>(ZS)) & 15)
     return fail(-2, "ptar_gwb_synth_i8: AS / ZS must be 16-byte aligned%s");
   if (n_tiles > 65535) return fail(-3, "ptar_gwb_synth_i8: more than 65535 tiles%s");
@@ -552,7 +552,7 @@ int ptar_run_job(const ptar_job* job, int64_t real0, int32_t nreal, double* out,
     if (i8) {   // tcgen05 path: exact int8 GEMMs on the digit slices, fp64 fix-up
       if (!job->colscale || !job->zscale || !job->tile_list_i8) return fail(-2, "ptar_run_job: tcgen05 GWB buffers missing%s");
       rc = ptar_gwb_synth_i8(job->Gbuf, g.g_ld, g.g_ldr, job->AS, job->colscale, job->ZS, job->zscale, g.n_psr, job->Jg, job->Jpad, nreal,
-                             job->rcap, job->tile_list_i8, job->n_syn_tiles, stream);
+                             job->rcap, job->tile_list_i8, job->n_syn_tiles_i8, stream);
     } else {
       rc = ptar_gwb_synth(job->Gbuf, g.g_ld, g.g_ldr, job->A, job->lda, job->Zm, job->Jg, nreal, job->tile_list, job->n_syn_tiles,
                           job->knots, job->lower_tri, stream);

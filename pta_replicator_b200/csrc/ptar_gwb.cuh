@@ -38,7 +38,7 @@ constexpr int MIX_JT = 32, MX_ROWS = 128, MX_ZS = MX_ROWS + 4, MX_GROUPS = 1;
 
 // SLICE = true (throughput mode with the tcgen05 synthesis, n_psr <= 72): instead of fp64 Zm the kernel emits the
 // six signed radix-256 digit slices of Zm[p][r][j] / zscale[p] in the tensor core's K-major core-matrix tile layout
-// (ptar_gwb_i8.cuh: ZS[slice][p][r-block][k-chunk][16][4][8][16]).  The accumulators of all n-tiles stay in registers,
+// (ptar_gwb_i8.cuh: ZS[slice][p][r-block][k-chunk of 32][16][2][8][16]).  The accumulators of all n-tiles stay in registers,
 // the digits are staged through the shared memory the draws occupied and leave as 16-byte stores.  Digit
 // extraction: m = fma(v, 2^48 / zscale, 1.5 * 2^52) holds round(v 2^48 / zscale) in its low mantissa bits; adding
 // 0x80 to every byte position turns the balanced digits d in [-128, 127] into the plain bytes d + 128 of that integer.
@@ -148,16 +148,17 @@ __global__ void __launch_bounds__(256, 2) gwb_mix_dmma_kernel(double* __restrict
         }
       }
       __syncthreads();
-      // 16-byte pieces: (p, slice, c, l) -> ZS[slice][p][rblk][kch][g][c][r8][16]; the four rows of a piece are adjacent
-      const int64_t n_rblk = rcap / 128, nkch = Jpad / 64;
-      const int kch = j0 / 64, c0 = (j0 % 64) / 16;
+      // 16-byte pieces: (p, slice, c, l) -> ZS[slice][p][rblk][kch][g][c][r8][16] (k-chunks of 32 columns = this CTA's
+      // 32 columns); the four rows of a piece are adjacent
+      const int64_t n_rblk = rcap / 128, nkch = Jpad / 32;
+      const int kch = j0 / 32;
       const int64_t rblk = rbase / 128;
       const int g = static_cast<int>((rbase % 128) / 8), r8 = static_cast<int>(rbase % 8);
       for (int idx = tid; idx < P * 6 * 2 * 4; idx += 256) {
         const int l = idx & 3, c = (idx >> 2) & 1, sl = (idx >> 3) % 6, p = idx / 48;
         const uint4 v = *reinterpret_cast<const uint4*>(ds + size_t(p) * MX_DSTRIDE + ((sl * 2 + c) * 4 + l) * 16);
         if (rbase + l < rcap && j0 + c * 16 < Jpad) {
-          int8_t* dst = ZS + ((((size_t(sl) * P + p) * n_rblk + rblk) * nkch + kch) * 16 + g) * 512 + ((c0 + c) * 8 + r8 + l) * 16;
+          int8_t* dst = ZS + ((((size_t(sl) * P + p) * n_rblk + rblk) * nkch + kch) * 16 + g) * 256 + (c * 8 + r8 + l) * 16;
           *reinterpret_cast<uint4*>(dst) = v;
         }
       }

@@ -16,15 +16,18 @@
 // Operand staging: the producers write both operands in the tensor core's canonical K-major no-swizzle layout
 // (8 rows x 16 bytes core matrices), tile by tile, so that one k-chunk of one operand is a single contiguous
 // bulk-async (TMA) copy:
-//   ZS  [slice s][pulsar p][r-block of 128][k-chunk of 64 j][16 row groups][4 x 16-byte k][8 rows][16 bytes]   (8 KB per copy)
-//   AS  [tile][k-chunk of 64 j][slice t][8 row groups][4][8][16]                                              (24 KB per copy)
-// One instruction multiplies Z slice s (128 realizations x 32 j) with the STACK of A slices t = 0..min(5, 6-s) (N = 64
-// per slice, split at N = 256) and lands in TMEM columns 64 (s + t) + knot: the stacking along N is what makes the
-// 26 slice products cost 9 instructions per 32-j step instead of 26.
+//   ZS  [slice s][pulsar p][r-block of 128][k-chunk of 32 j][16 row groups][2 x 16-byte k][8 rows][16 bytes]   (4 KB per copy)
+//   AS  [tile][k-chunk of 32 j][slice t][4 row groups][2][8][16]                                              (6 KB per copy)
+// One instruction multiplies Z slice s (128 realizations x 32 j) with the STACK of A slices t = 0..min(5, 6-s) (N = 32
+// per slice, up to 192) and lands in TMEM columns 32 (s + t) + knot: the stacking along N is what makes the 26 slice
+// products cost 7 instructions per 32-j step instead of 26.
 //
-// CTA = 256 threads: warp 0 lane 0 issues the bulk copies (3-stage mbarrier ring, 72 KB per stage), warp 1 allocates
-// TMEM (512 columns) and its lane 0 issues the MMAs; then all 8 warps run the epilogue (warp w reads TMEM lanes
-// 32 (w % 4).. and the knots 32 (w / 4)..).  Measured phase times per CTA: tools/i8_timeline.py.
+// CTA = one tile of 32 knots x 128 realizations, 256 threads: warp 0 lane 0 issues the bulk copies (3-stage mbarrier
+// ring, 30 KB per stage), warp 1 allocates TMEM (256 columns) and its lane 0 issues the MMAs; then all 8 warps run the
+// epilogue (warp w reads TMEM lanes 32 (w % 4).. and the knots 16 (w / 4)..).  92 KB of shared memory and half the
+// tensor memory: TWO CTAs per SM, so the prologue (set-up, first copies) and the epilogue of one tile run under the
+// main loop of the other -- with one 64-knot tile per SM (7 x 64 = 448 accumulator columns) they were 45 % of the
+// kernel (measured per phase with tools/i8_timeline.py).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -34,13 +37,13 @@ namespace ptar {
 constexpr int I8_SLICES = 6;          // digits per operand
 constexpr int I8_DIAGS = 7;           // kept weights d = s + t = 0 .. 6
 constexpr int I8_BM = 128;            // realizations per CTA (MMA M)
-constexpr int I8_BN = 64;             // knots per CTA
-constexpr int I8_BK = 64;             // j per pipeline stage (bytes, int8)
+constexpr int I8_BN = 32;             // knots per CTA
+constexpr int I8_BK = 32;             // j per pipeline stage (bytes, int8) = the K of one MMA
 constexpr int I8_STAGES = 3;
-constexpr int I8_A_BYTES = I8_BM * I8_BK;                 // one Z slice of one stage: 8 KB
-constexpr int I8_B_BYTES = I8_SLICES * I8_BN * I8_BK;     // all A slices of one stage: 24 KB
-constexpr int I8_STAGE_BYTES = I8_SLICES * I8_A_BYTES + I8_B_BYTES;   // 72 KB
-constexpr int I8_TMEM_COLS = 512;                         // 7 diagonals x 64 knots = 448 used
+constexpr int I8_A_BYTES = I8_BM * I8_BK;                 // one Z slice of one stage: 4 KB
+constexpr int I8_B_BYTES = I8_SLICES * I8_BN * I8_BK;     // all A slices of one stage: 6 KB
+constexpr int I8_STAGE_BYTES = I8_SLICES * I8_A_BYTES + I8_B_BYTES;   // 30 KB
+constexpr int I8_TMEM_COLS = 256;                         // 7 diagonals x 32 knots = 224 used
 constexpr int I8_THREADS = 256;
 constexpr size_t I8_SMEM = size_t(I8_STAGES) * I8_STAGE_BYTES + 128;   // + barriers, tmem address
 
@@ -131,10 +134,10 @@ __global__ void __launch_bounds__(256) gwb_slice_kernel(int8_t* __restrict__ ZS,
   }
   const int64_t rblk = r / I8_BM;
   const int g = static_cast<int>((r % I8_BM) / 8);
-  const int kch = piece / 4, c = piece % 4;
+  const int kch = piece / 2, c = piece % 2;
   const int64_t nkch = Jpad / I8_BK;
   const int64_t n_rblk = rcap / I8_BM;
-  const size_t tile_off = ((((rblk * nkch + kch) * 16 + g) * 4 + c) * 8 + r8) * 16;
+  const size_t tile_off = ((((rblk * nkch + kch) * 16 + g) * 2 + c) * 8 + r8) * 16;
 #pragma unroll
   for (int s = 0; s < I8_SLICES; ++s) {
     int8_t* dst = ZS + ((size_t(s) * P + p) * n_rblk) * (nkch * I8_A_BYTES) + tile_off;
@@ -149,9 +152,9 @@ __device__ long long* g_i8_dbg = nullptr;
 
 // ---------------------------------------------------------------------------------------------------------------
 // grid = (r-blocks, tiles); the r-block index is fastest so the CTAs that share a tile's A slices run together.
-// tile_list[tile] = {pulsar, first compact column, columns (<= 64), k extent}; AS tile index = blockIdx.y (the host
+// tile_list[tile] = {pulsar, first compact column, columns (<= 32), k extent}; AS tile index = blockIdx.y (the host
 // builds AS in tile_list order).  colscale[q] = sA[knot(q)] * 2^-16; zscale[p] = sZ[p].
-__global__ void __launch_bounds__(I8_THREADS, 1)
+__global__ void __launch_bounds__(I8_THREADS, 2)
 gwb_synth_i8_kernel(double* __restrict__ G, int64_t g_ld, int64_t g_ldr, const int8_t* __restrict__ AS, const double* __restrict__ colscale,
                     const int8_t* __restrict__ ZS, const double* __restrict__ zscale, int P, int J, int Jpad, int64_t nreal,
                     int64_t rcap, const int32_t* __restrict__ tile_list) {
@@ -166,7 +169,7 @@ gwb_synth_i8_kernel(double* __restrict__ G, int64_t g_ld, int64_t g_ldr, const i
   const int32_t* tl = tile_list + size_t(blockIdx.y) * 4;
   const int p = tl[0], kn0 = tl[1], kcnt = tl[2];
   const int kend = min(J, tl[3]);
-  const int nk = (kend + I8_BK - 1) / I8_BK;               // k-chunks of 64 with a non-zero A column
+  const int nk = (kend + I8_BK - 1) / I8_BK;               // k-chunks of 32 with a non-zero A column
   const int64_t rblk = blockIdx.x;
   const int64_t nkch = Jpad / I8_BK;
   const int64_t n_rblk = rcap / I8_BM;
@@ -232,23 +235,20 @@ gwb_synth_i8_kernel(double* __restrict__ G, int64_t g_ld, int64_t g_ldr, const i
       if (dbg && kc == 0) dbg[3] = clock64();
       const uint32_t sa = i8_smem_u32(stage_base + size_t(st) * I8_STAGE_BYTES);
       const uint32_t sbm = sa + I8_SLICES * I8_A_BYTES;
-      // stage layout of one operand: [row group][4 k-pieces of 16 B][8 rows][16 B]: lbo = 128, sbo = 512
+      // stage layout of one operand: [row group][2 k-pieces of 16 B][8 rows][16 B]: lbo = 128, sbo = 256; one MMA
+      // consumes the 32 bytes of K of a stage
+      const uint32_t first = (kc == 0) ? 0u : 1u;
+      // (Z slice s, first A slice t0, A slices taken, opens): TMEM columns 32 (s + t0) ..; an instruction either
+      // overwrites all its columns (first k-chunk only) or accumulates into all of them, so the slice that first
+      // touches diagonal 6 (s = 1, t = 5) is issued on its own
+      constexpr int kPlan[7][4] = {{0, 0, 6, 1}, {1, 0, 5, 0}, {1, 5, 1, 1}, {2, 0, 5, 0}, {3, 0, 4, 0}, {4, 0, 3, 0}, {5, 0, 2, 0}};
 #pragma unroll
-      for (int kk = 0; kk < I8_BK / 32; ++kk) {          // one MMA consumes 32 bytes of K = two 16-byte pieces
-        const uint32_t first = (kc == 0 && kk == 0) ? 0u : 1u;
-        // (Z slice s, first A slice t0, A slices taken, opens): columns 64 (s + t0) .. ; N <= 256 per instruction; an
-        // instruction either overwrites all its columns (first k-step only) or accumulates into all of them, so the
-        // slice that first touches diagonal 6 (s = 1, t = 5) is issued on its own
-        constexpr int kPlan[10][4] = {{0, 0, 4, 1}, {0, 4, 2, 1}, {1, 0, 4, 0}, {1, 4, 1, 0}, {1, 5, 1, 1},
-                                      {2, 0, 4, 0}, {2, 4, 1, 0}, {3, 0, 4, 0}, {4, 0, 3, 0}, {5, 0, 2, 0}};
-#pragma unroll
-        for (int q = 0; q < 10; ++q) {
-          const int s = kPlan[q][0], t0 = kPlan[q][1], take = kPlan[q][2];
-          const uint64_t adesc = i8_smem_desc(sa + s * I8_A_BYTES + kk * 256, 128, 512);
-          const uint64_t bdesc = i8_smem_desc(sbm + t0 * (I8_BN * I8_BK) + kk * 256, 128, 512);
-          const uint32_t dcol = tmem_base + uint32_t((s + t0) * I8_BN);
-          i8_mma(dcol, adesc, bdesc, i8_instr_desc(take * I8_BN), kPlan[q][3] ? first : 1u);
-        }
+      for (int q = 0; q < 7; ++q) {
+        const int s = kPlan[q][0], t0 = kPlan[q][1], take = kPlan[q][2];
+        const uint64_t adesc = i8_smem_desc(sa + s * I8_A_BYTES, 128, 256);
+        const uint64_t bdesc = i8_smem_desc(sbm + t0 * (I8_BN * I8_BK), 128, 256);
+        const uint32_t dcol = tmem_base + uint32_t((s + t0) * I8_BN);
+        i8_mma(dcol, adesc, bdesc, i8_instr_desc(take * I8_BN), kPlan[q][3] ? first : 1u);
       }
       i8_umma_commit(empty + st);                        // frees the stage once these MMAs have read it
     }
@@ -257,7 +257,7 @@ gwb_synth_i8_kernel(double* __restrict__ G, int64_t g_ld, int64_t g_ldr, const i
   }
 
   // ---- epilogue: all 8 warps.  Warp w reads TMEM lanes 32 (w % 4) .. +31 (= realizations of this r-block) and the
-  // knots 32 (w / 4) .. +31; the loads of diagonal d + 1 are in flight while diagonal d is folded in.
+  // knots 16 (w / 4) .. +15; the loads of diagonal d + 1 are in flight while diagonal d is folded in.
   {
     const int quarter = warp & 3, half = warp >> 2;
     const int64_t r = rblk * I8_BM + quarter * 32 + lane;
@@ -265,32 +265,29 @@ gwb_synth_i8_kernel(double* __restrict__ G, int64_t g_ld, int64_t g_ldr, const i
     __syncwarp();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (dbg && tid == 64) dbg[5] = clock64();
-#define I8_TMEM_LD32(v, addr)                                                                                                 \
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                     \
-               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                     \
-               "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                     \
+#define I8_TMEM_LD16(v, addr)                                                                                                 \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                                     \
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"                              \
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),   \
-                 "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),        \
-                 "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),       \
-                 "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                     \
+                 "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])                      \
                : "r"(addr))
-    double val[32];
+    double val[16];
 #pragma unroll
-    for (int n = 0; n < 32; ++n) val[n] = 0.0;
+    for (int n = 0; n < 16; ++n) val[n] = 0.0;
     if (nk > 0) {
-      const uint32_t tbase = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(half * 32);
-      uint32_t va[32], vb[32];
-      I8_TMEM_LD32(va, tbase);
+      const uint32_t tbase = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(half * 16);
+      uint32_t va[16], vb[16];
+      I8_TMEM_LD16(va, tbase);
       double w = 1.0;
 #pragma unroll
       for (int d = 0; d < I8_DIAGS; ++d) {
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (d + 1 < I8_DIAGS) {
-          if (d & 1) { I8_TMEM_LD32(va, tbase + uint32_t((d + 1) * I8_BN)); }
-          else       { I8_TMEM_LD32(vb, tbase + uint32_t((d + 1) * I8_BN)); }
+          if (d & 1) { I8_TMEM_LD16(va, tbase + uint32_t((d + 1) * I8_BN)); }
+          else       { I8_TMEM_LD16(vb, tbase + uint32_t((d + 1) * I8_BN)); }
         }
 #pragma unroll
-        for (int n = 0; n < 32; ++n) {
+        for (int n = 0; n < 16; ++n) {
           // int32 -> double without the conversion pipe: 2^52 + 2^31 + x sits exactly in the mantissa of {0x43300000, x ^ 2^31}
           const uint32_t vi = (d & 1) ? vb[n] : va[n];
 #ifdef I8_EPI_NOMATH
@@ -303,20 +300,20 @@ gwb_synth_i8_kernel(double* __restrict__ G, int64_t g_ld, int64_t g_ldr, const i
         w *= 0.00390625;                                 // 2^-8 per diagonal
       }
     }
-#undef I8_TMEM_LD32
+#undef I8_TMEM_LD16
 #ifdef I8_EPI_NOSTORE
     if (r < nreal && val[5] == 1.2345e-300) {
 #else
     if (r < nreal) {
 #endif
       // column-major grid G[kn0 + n][r]: the 32 lanes of a warp are 32 consecutive realizations -> one 256-byte store per
-      // knot (row-major stores of a thread's 32 knots were 16 bytes per 32-byte sector: 5.9k of the 8.4k epilogue clocks)
+      // knot (row-major stores of a thread's knots were 16 bytes per 32-byte sector and cost 5.9k clk per tile)
       const int kpad = (kcnt + 1) & ~1;
-      double* gcol = G + size_t(kn0 + half * 32) * g_ldr + r;
-      const double* cs = s_colscale + half * 32;
+      double* gcol = G + size_t(kn0 + half * 16) * g_ldr + r;
+      const double* cs = s_colscale + half * 16;
 #pragma unroll
-      for (int n = 0; n < 32; ++n) {
-        if (half * 32 + n < kpad) gcol[size_t(n) * g_ldr] = val[n] * cs[n];
+      for (int n = 0; n < 16; ++n) {
+        if (half * 16 + n < kpad) gcol[size_t(n) * g_ldr] = val[n] * cs[n];
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -37,7 +37,7 @@ def _both_syntheses(b, R, seed=5, real0=8):
                                  job.knots, job.lower_tri, stream), "synth")
     _cabi.check(L.ptar_gwb_slice_i8(job.ZS, job.Zm, job.zinv, b.n_psr, job.Jg, job.Jpad, R, job.rcap, stream), "slice")
     _cabi.check(L.ptar_gwb_synth_i8(Gi.data_ptr(), st["g_ld"], ldr, job.AS, job.colscale, job.ZS, job.zscale, b.n_psr, job.Jg, job.Jpad,
-                                    R, job.rcap, job.tile_list_i8, job.n_syn_tiles, stream), "synth_i8")
+                                    R, job.rcap, job.tile_list_i8, job.n_syn_tiles_i8, stream), "synth_i8")
     torch.cuda.synchronize()
     # the grid is column-major [g_ld][g_ldr]: return [R, g_ld] views
     return Gd.view(-1, ldr)[:, :R].T, Gi.view(-1, ldr)[:, :R].T, job, keep, st
@@ -72,15 +72,15 @@ def test_digit_slices_match_the_host_restatement():
     P, Jg, Jpad, rcap = b.n_psr, job.Jg, job.Jpad, job.rcap
     Zm = [k for k in keep if k.dtype == torch.float64 and k.numel() == R * P * Jg][0].view(P, R, Jg).cpu().numpy()
     ZS = [k for k in keep if k.dtype == torch.int8][0].cpu().numpy()
-    ZS = ZS.reshape(_cabi.I8_SLICES, P, rcap // 128, Jpad // 64, 16, 4, 8, 16)
+    ZS = ZS.reshape(_cabi.I8_SLICES, P, rcap // 128, Jpad // 32, 16, 2, 8, 16)
     zscale = st["i8_zscale"].cpu().numpy()
     for p in (0, P - 1):
-        for rblk, kch in ((0, 0), (1, 9), (0, 4)):
+        for rblk, kch in ((0, 0), (1, 18), (0, 9)):
             tile = ZS[:, p, rblk, kch]                                  # [s][g][c][r8][16]
-            dig = tile.transpose(0, 1, 3, 2, 4).reshape(_cabi.I8_SLICES, 128, 64)   # [s][row][k]
+            dig = tile.transpose(0, 1, 3, 2, 4).reshape(_cabi.I8_SLICES, 128, 32)   # [s][row][k]
             rows = np.arange(rblk * 128, min(rblk * 128 + 128, R))
-            cols = np.arange(kch * 64, min(kch * 64 + 64, Jg))
-            x = np.zeros((128, 64))
+            cols = np.arange(kch * 32, min(kch * 32 + 32, Jg))
+            x = np.zeros((128, 32))
             x[:len(rows), :len(cols)] = Zm[p][rows][:, cols] / zscale[p]
             ref = PulsarBatch.radix256_digits(x)
             assert np.array_equal(dig[:, :len(rows)], ref[:, :len(rows)]), (p, rblk, kch)
@@ -104,14 +104,13 @@ def test_fused_mixing_emits_the_same_digit_slices():
                                             _cabi.current_stream()), "mix_i8")
     torch.cuda.synchronize()
     P, Jpad, rcap = b.n_psr, job.Jpad, job.rcap
-    a = ZS.view(_cabi.I8_SLICES, P, rcap // 128, Jpad // 64, 16, 4, 8, 16).cpu().numpy()
-    r = ref.view(_cabi.I8_SLICES, P, rcap // 128, Jpad // 64, 16, 4, 8, 16).cpu().numpy()
-    # rows of realizations < R and columns j < 608 (19 blocks of 32) are written by both
+    a = ZS.view(_cabi.I8_SLICES, P, rcap // 128, Jpad // 32, 16, 2, 8, 16).cpu().numpy()
+    r = ref.view(_cabi.I8_SLICES, P, rcap // 128, Jpad // 32, 16, 2, 8, 16).cpu().numpy()
+    # rows of realizations < R are written by both (all Jpad = 608 columns: 19 blocks of 32)
     rows = np.arange(rcap).reshape(rcap // 128, 16, 8)          # [rblk][g][r8] -> realization
     ok_rows = rows < R
-    for kch in range(Jpad // 64):
-        ncs = 4 if kch * 64 + 64 <= 608 else (608 - kch * 64) // 16
-        x, y = a[:, :, :, kch, :, :ncs], r[:, :, :, kch, :, :ncs]       # [s][p][rblk][g][c][r8][16]
+    for kch in range(Jpad // 32):
+        x, y = a[:, :, :, kch], r[:, :, :, kch]                      # [s][p][rblk][g][c][r8][16]
         m = np.broadcast_to(ok_rows[None, None, :, :, None, :, None], x.shape)
         assert np.array_equal(x[m], y[m]), kch
 

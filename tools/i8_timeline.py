@@ -17,7 +17,7 @@ synthetic.ng15_recipe(b, noise, white=False, ecorr=False, red=False)
 st = b.compile()
 R = 1000
 b.generate(R, seed=1)
-buf = torch.zeros(st["n_syn_tiles"] * 8, dtype=torch.int64, device=b.device)
+buf = torch.zeros(int(st["i8_tiles"].shape[0]) * 8, dtype=torch.int64, device=b.device)
 _cabi.check(_cabi.lib().ptar_debug_i8_timestamps(buf.data_ptr()))
 b.generate(R, seed=1)
 torch.cuda.synchronize()
@@ -31,5 +31,6 @@ for i, n in enumerate(names, start=1):
     d = t[:, i] - base
     print(f"  {n:32s} median {np.median(d):9.0f}  p10 {np.quantile(d, 0.1):9.0f}  p90 {np.quantile(d, 0.9):9.0f} clk since CTA start")
 per = (t[:, 5] - t[:, 3]) / np.maximum(t[:, 7], 1)
-print(f"  mainloop clk per 64-j chunk (first stage landed -> accumulators complete): median {np.median(per):.0f} (MMA floor 1664)")
+print(f"  mainloop clk per 32-column chunk (first stage landed -> accumulators complete): median {np.median(per):.0f} "
+      "(MMA floor 416 for one CTA alone; two CTAs share the SM's tensor core)")
 print(f"  epilogue: median {np.median(t[:, 6] - t[:, 5]):.0f} clk")
