@@ -332,6 +332,24 @@ def config5_block(args, world, rank, dist, hbm):
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         ok = int(t.item())
     recv = (world - 1) * padded / world * b.ld * 8.0           # bytes every GPU receives
+    sweep = {}
+    if world > 1:      # how the overlapped gather depends on the chunk size (same work, same ownership pattern)
+        for ch in (128, 2048):
+            Cs, ncs, pads = D.gather_plan(nreal, world, ch)
+            if pads > full.shape[0]:
+                full = torch.empty((pads, b.ld), dtype=torch.float64, device=b.device)
+            for rep in range(2):
+                torch.cuda.synchronize()
+                dist.barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                D.generate_gathered(b, nreal, seed=SEED, chunk=ch, out=full, gather=True, comm_stream=comm)
+                e1.record()
+                torch.cuda.synchronize()
+                dist.barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=b.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sweep[str(Cs)] = {"value_with_gather": pads / (float(t.item()) * 1e-3), "ms": float(t.item()), "chunks": ncs}
     blk = {"workload": workload_name("5", kind, b) + f"; {nreal} realizations strong-scaled over {world} GPU(s), chunk-interleaved ownership, "
                        f"{C} realizations per rank per chunk x {n_chunks} chunks ({padded} generated)",
            "value_without_gather": padded / (res[False] * 1e-3), "value_with_gather": padded / (res[True] * 1e-3),
@@ -339,6 +357,8 @@ def config5_block(args, world, rank, dist, hbm):
            "gathered_bytes_per_gpu": b.ld * 8.0 * padded, "gather_overlap": "NCCL all_gather_into_tensor of chunk c on a second stream while "
            "chunk c+1 is generated (two staging buffers)", "shard_bitwise_ok": bool(ok)}
     if world > 1:
+        blk["chunk_sweep"] = sweep
+        blk["nccl"] = {"high_priority_stream": os.environ.get("TORCH_NCCL_HIGH_PRIORITY", "")}
         blk["recv_GBps_per_gpu"] = recv / (res[True] * 1e-3) / 1e9
         blk["nvlink_frac_of_measured_peer_copy"] = blk["recv_GBps_per_gpu"] / NVLINK_PEER_GBS
         blk["gather_bound_ceiling"] = {"realizations_per_s": padded / (recv / (NVLINK_PEER_GBS * 1e9)),
@@ -405,6 +425,9 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # the NCCL kernels of the overlapped all-gather run next to a generator that fills every SM: give them a
+        # high-priority stream so their CTAs are scheduled as soon as generator CTAs retire
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if rank == 0 and not os.environ.get("PTAR_B200_LIB"):
         ge.build()               # no-op when the in-tree .so is up to date
