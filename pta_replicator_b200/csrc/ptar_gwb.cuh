@@ -57,9 +57,8 @@ __global__ void __launch_bounds__(256, 2) gwb_mix_dmma_kernel(double* __restrict
   double* ms = mx_smem + size_t(KP) * MX_ZS;  // [NP][MS]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int j0 = blockIdx.x * MIX_JT;
-  for (int idx = tid; idx < NP * MS; idx += 256) {
-    const int p = idx / MS, q = idx % MS;
-    ms[idx] = (p < P && q <= p) ? __ldg(M + size_t(p) * P + q) : 0.0;
+  for (int p = tid >> 5; p < NP; p += 8) {      // warp per row of M: no integer division by the run-time pitch
+    for (int q = tid & 31; q < MS; q += 32) ms[p * MS + q] = (p < P && q <= p) ? __ldg(M + size_t(p) * P + q) : 0.0;
   }
   const int fr = lane >> 2, fk = lane & 3;
   const int row0 = warp * 16;
