@@ -135,3 +135,33 @@ def test_generator_with_tcgen05_synthesis_equals_the_fp64_path(kind):
         worst = max(worst, ((got[:, sl] - ref[:, sl]).abs().max() / ref[:, sl].std()).item())
     print(f"generator with tcgen05 synthesis vs fp64 ({kind}): max|d|/rms = {worst:.3e}")
     assert worst < I8, worst
+
+
+def _array_pulsars(n, ntoa=24, seed=3):
+    import pta_replicator_b200 as P
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n):
+        mjd = np.sort(rng.uniform(53000, 58800, ntoa)).astype(np.longdouble)
+        p = P.pulsar_from_arrays(f"J{i:04d}+00", {"RAJ": float(rng.uniform(0, 24)), "DECJ": float(np.degrees(np.arcsin(rng.uniform(-1, 1))))},
+                                 mjd, rng.uniform(0.1, 1.0, ntoa))
+        P.make_ideal(p)
+        out.append(p)
+    return out
+
+
+@pytest.mark.parametrize("npsr,npts,howml", [(80, 600, 10), (5, 301, 4), (3, 130, 10)])
+def test_tcgen05_path_for_large_arrays_and_odd_grids(npsr, npts, howml):
+    """More than 72 pulsars (the mixing kernel then writes fp64 Zm and ptar_gwb_slice_i8 makes the digits: the unfused
+    route inside generate()) and grid lengths that are not multiples of 32 (the last k-chunk is zero padded)."""
+    from pta_replicator_b200.engine import PulsarBatch
+    b = PulsarBatch(_array_pulsars(npsr))
+    b.set_gwb(-14.3, 13.0 / 3.0, npts=npts, howml=howml)
+    R = 150
+    b.use_tcgen05 = False
+    ref = b.generate(R, seed=9, real0=4)
+    b.use_tcgen05 = True
+    got = b.generate(R, seed=9, real0=4)
+    err = ((got - ref).abs().max() / ref.std()).item()
+    print(f"tcgen05 vs fp64 path, {npsr} psr, npts = {npts}: max|d|/rms = {err:.3e}")
+    assert float(ref.std()) > 0 and err < I8, err
