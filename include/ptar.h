@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define PTAR_VERSION 100  /* major*100 + minor */
+#define PTAR_VERSION 200  /* major*100 + minor; 2.0: column-major grid, g_ldr / c_rows, tcgen05 GWB entry points, pshift phases */
 
 /* Geometry limits of the fused generator kernel. */
 #define PTAR_TILE_TOAS   1024  /* TOAs per tile (256 threads x 4)            */

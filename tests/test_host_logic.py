@@ -21,7 +21,7 @@ def test_cabi_exports_every_declared_symbol():
     L = _cabi.lib()
     for name in declared:
         assert hasattr(L, name)
-    assert L.ptar_version() == 100
+    assert L.ptar_version() == 200
 
 
 def test_no_cpu_fallback_without_a_gpu():
