@@ -112,7 +112,7 @@ def test_planner_epochs_and_tiles():
         P.make_ideal(p)
         psrs.append(p)
     for exact in (False, True):
-        b = PulsarBatch(psrs, plan_only=True, exact_epochs=exact)
+        b = PulsarBatch(psrs, plan_only=True, exact_epochs=exact, rn_taylor_tol=1e-14)   # 1e-14: three Taylor terms
         for i, s in enumerate(spec):
             b.set_white(i, efac=s["efac"], log10_equad=s["l10_equad"], flags=np.array(s["backends"]))
             b.set_ecorr(i, s["l10_ecorr"], flags=np.array(s["backends"]), coarsegrain=1.0 / 86400.0)
