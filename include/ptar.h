@@ -253,6 +253,18 @@ typedef struct {
   int32_t n_syn_tiles_i8;
 } ptar_job;
 
+/* Peer delivery over NVLink without a collective library (multi-GPU row of SURVEY.md 8e; the reference has no
+ * distributed code): a rank exports its result buffer (CUDA IPC), every other rank maps it into its own address space
+ * and pushes its realization chunks straight into it with the copy engines, overlapped with generation.
+ * ptar_peer_export: handle_host[64] <- IPC handle of the allocation that contains dev_ptr, *offset <- dev_ptr - base.
+ * ptar_peer_open:   maps an exported allocation into the current device's context (lazy peer access); *base_out is the
+ *                   mapped base (add the exporter's offset); ptar_peer_close unmaps it.
+ * ptar_peer_copy:   asynchronous device-to-device copy (UVA) between local and mapped peer memory on `stream`. */
+int ptar_peer_export(const void* dev_ptr, void* handle_host, int64_t* offset);
+int ptar_peer_open(const void* handle_host, void** base_out);
+int ptar_peer_close(void* base);
+int ptar_peer_copy(void* dst, const void* src, int64_t bytes, void* stream);
+
 int ptar_run_job(const ptar_job* job, int64_t real0, int32_t nreal, double* out, void* stream);
 int ptar_run_job_to_host(const ptar_job* job, int64_t real0, int64_t nreal, int32_t chunk,
                          double* out_host, double* dev_buf0, double* dev_buf1, void* stream0, void* stream1);

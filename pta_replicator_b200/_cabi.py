@@ -22,7 +22,7 @@ F_WHITE, F_ECORR, F_RED, F_GWB, F_DET, F_WHITE1 = 1, 2, 4, 8, 16, 32
 K_WHITE1, K_WHITE2, K_ECORR, K_RED, K_GWB = 1, 2, 3, 4, 5
 
 EXPORTS = ("ptar_version", "ptar_last_error", "ptar_cholesky_lower", "ptar_fourier_basis", "ptar_cgw_delay", "ptar_cw_catalog", "ptar_burst_delay", "ptar_memory_delay",
-           "ptar_gwb_mix", "ptar_gwb_synth", "ptar_gwb_mix_i8", "ptar_gwb_slice_i8", "ptar_gwb_synth_i8", "ptar_debug_i8_timestamps", "ptar_generate", "ptar_generate_stage", "ptar_philox_normals", "ptar_run_job",
+           "ptar_gwb_mix", "ptar_gwb_synth", "ptar_gwb_mix_i8", "ptar_gwb_slice_i8", "ptar_gwb_synth_i8", "ptar_debug_i8_timestamps", "ptar_generate", "ptar_generate_stage", "ptar_philox_normals", "ptar_peer_export", "ptar_peer_open", "ptar_peer_close", "ptar_peer_copy", "ptar_run_job",
            "ptar_run_job_to_host")
 
 
@@ -91,6 +91,10 @@ def lib():
     L.ptar_generate.argtypes = [C.POINTER(GenParams), vp]
     L.ptar_generate_stage.argtypes = [C.POINTER(GenParams), i32, vp]
     L.ptar_philox_normals.argtypes = [vp, i32, i32, i64, i64, i64, u64, vp]
+    L.ptar_peer_export.argtypes = [vp, vp, C.POINTER(C.c_int64)]
+    L.ptar_peer_open.argtypes = [vp, C.POINTER(C.c_void_p)]
+    L.ptar_peer_close.argtypes = [vp]
+    L.ptar_peer_copy.argtypes = [vp, vp, i64, vp]
     L.ptar_run_job.argtypes = [C.POINTER(Job), i64, C.c_int32, vp, vp]
     L.ptar_run_job_to_host.argtypes = [C.POINTER(Job), i64, i64, C.c_int32, vp, vp, vp, vp, vp]
     for name in EXPORTS:

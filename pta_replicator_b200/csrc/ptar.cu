@@ -526,6 +526,57 @@ int ptar_philox_normals(float* out, int kind, int psr, int64_t realization, int6
   return check_launch("ptar_philox_normals");
 }
 
+int ptar_peer_export(const void* dev_ptr, void* handle_host, int64_t* offset) {
+  if (!dev_ptr || !handle_host || !offset) return fail(-1, "ptar_peer_export: bad argument%s");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+  cudaPointerAttributes attr;
+  cudaError_t e = cudaPointerGetAttributes(&attr, dev_ptr);
+  if (e != cudaSuccess || attr.type != cudaMemoryTypeDevice) return fail(-2, "ptar_peer_export: not a device pointer%s");
+  // the handle describes the whole allocation: find its base with the driver's range query (through the runtime's
+  // driver entry point, so that libcuda need not be linked)
+  typedef int (*range_fn)(unsigned long long*, size_t*, unsigned long long);
+  static range_fn get_range = nullptr;
+  if (!get_range) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    e = cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr);
+    if (e != cudaSuccess || !fn) return fail(-100, "ptar_peer_export: cuMemGetAddressRange unavailable%s");
+    get_range = reinterpret_cast<range_fn>(fn);
+  }
+  unsigned long long base = 0;
+  size_t size = 0;
+  if (get_range(&base, &size, reinterpret_cast<unsigned long long>(dev_ptr)) != 0)
+    return fail(-100, "ptar_peer_export: cuMemGetAddressRange failed%s");
+  e = cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle_host), reinterpret_cast<void*>(base));
+  if (e != cudaSuccess) return fail(-100, "ptar_peer_export: cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+  *offset = static_cast<int64_t>(reinterpret_cast<unsigned long long>(dev_ptr) - base);
+  return 0;
+}
+
+int ptar_peer_open(const void* handle_host, void** base_out) {
+  if (!handle_host || !base_out) return fail(-1, "ptar_peer_open: bad argument%s");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle_host, sizeof(h));
+  const cudaError_t e = cudaIpcOpenMemHandle(base_out, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return fail(-100, "ptar_peer_open: cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int ptar_peer_close(void* base) {
+  if (!base) return 0;
+  const cudaError_t e = cudaIpcCloseMemHandle(base);
+  if (e != cudaSuccess) return fail(-100, "ptar_peer_close: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int ptar_peer_copy(void* dst, const void* src, int64_t bytes, void* stream) {
+  if (!dst || !src || bytes < 0) return fail(-1, "ptar_peer_copy: bad argument%s");
+  if (bytes == 0) return 0;
+  const cudaError_t e = cudaMemcpyAsync(dst, src, static_cast<size_t>(bytes), cudaMemcpyDefault, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(-100, "ptar_peer_copy: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 int ptar_run_job(const ptar_job* job, int64_t real0, int32_t nreal, double* out, void* stream) {
   if (!job || !out || nreal <= 0) return fail(-1, "ptar_run_job: bad argument%s");
   ptar_gen_params g = job->gen;

@@ -147,6 +147,96 @@ def generate_gathered(batch, nreal: int, seed: int = 0, chunk: int = 512, group=
     return out
 
 
+class PeerDelivery:
+    """All-gather without a collective library: every rank maps the result buffer of every other rank into its own
+    address space (CUDA IPC through ``ptar_peer_export`` / ``ptar_peer_open``) and PUSHES the rows it generates
+    straight into them with the copy engines over NVLink (``ptar_peer_copy`` = an asynchronous UVA device-to-device
+    copy) on side streams, while the generator already produces the next chunk.  No SM is taken from the generator
+    (NCCL's all-gather kernels run on SMs), no staging buffers: a chunk is generated into its rows of the local
+    result and copied from there.  Rank r sends to r+1, r+2, ... so that at any moment every GPU receives from one
+    peer.  Rows are complete on every rank after ``finish()`` (stream sync + barrier)."""
+
+    def __init__(self, full, group=None, n_streams: int = 2):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from . import _cabi
+        self.torch, self.dist, self.group, self.lib = torch, dist, group, _cabi.lib()
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.full = full
+        handle = (C.c_ubyte * 64)()
+        off = C.c_int64(0)
+        _cabi.check(self.lib.ptar_peer_export(full.data_ptr(), handle, C.byref(off)), "ptar_peer_export")
+        mine = (bytes(handle), int(off.value), tuple(full.shape))
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=group)
+        self.bases, self.ptrs = {}, {}
+        for r, (h, o, shape) in enumerate(everyone):
+            if r == self.rank:
+                continue
+            if shape != tuple(full.shape):
+                raise ValueError("PeerDelivery: result buffers differ in shape between ranks")
+            base = C.c_void_p()
+            buf = (C.c_ubyte * 64).from_buffer_copy(h)
+            _cabi.check(self.lib.ptar_peer_open(buf, C.byref(base)), "ptar_peer_open")
+            self.bases[r], self.ptrs[r] = base.value, base.value + o
+        self.streams = [torch.cuda.Stream(full.device) for _ in range(max(1, n_streams))]
+        self.row_bytes = full.shape[1] * full.element_size()
+
+    def push_rows(self, row0: int, nrows: int, after_event):
+        """Copy rows [row0, row0 + nrows) of the local result into every peer's result, once ``after_event`` (recorded
+        on the generating stream) has completed."""
+        src = self.full.data_ptr() + row0 * self.row_bytes
+        from . import _cabi
+        for k in range(1, self.world):
+            r = (self.rank + k) % self.world
+            st = self.streams[k % len(self.streams)]
+            st.wait_event(after_event)
+            _cabi.check(self.lib.ptar_peer_copy(self.ptrs[r] + row0 * self.row_bytes, src, nrows * self.row_bytes, st.cuda_stream),
+                        "ptar_peer_copy")
+
+    def finish(self):
+        """All pushes of all ranks have landed when this returns."""
+        for st in self.streams:
+            st.synchronize()
+        self.torch.cuda.synchronize(self.full.device)
+        self.dist.barrier(group=self.group)
+
+    def close(self):
+        for r, base in list(self.bases.items()):
+            self.lib.ptar_peer_close(base)
+        self.bases.clear()
+        self.ptrs.clear()
+
+
+def generate_gathered_p2p(batch, nreal: int, seed: int = 0, chunk: int = 512, group=None, out=None, delivery=None, **kw):
+    """``generate_gathered`` with the all-gather replaced by peer pushes (``PeerDelivery``): same ownership, same
+    result (rows in global-id order on every rank).  Pass ``delivery`` (built once on ``out``) to reuse the IPC
+    mappings across calls."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    C, n_chunks, padded = gather_plan(nreal, world, chunk)
+    if out is None:
+        out = torch.empty((padded, batch.ld), dtype=torch.float64, device=batch.device)
+    own = delivery is None
+    if own:
+        delivery = PeerDelivery(out, group)
+    elif delivery.full.data_ptr() != out.data_ptr():
+        raise ValueError("generate_gathered_p2p: `delivery` was built on a different buffer")
+    main = torch.cuda.current_stream(batch.device)
+    for c in range(n_chunks):
+        r0 = chunk_ids(c, rank, world, C)
+        batch.generate(C, seed=seed, real0=r0, out=out[r0:r0 + C], **kw)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        delivery.push_rows(r0, C, ev)
+    delivery.finish()
+    if own:
+        delivery.close()
+    return out
+
+
 def bind_to_gpu_numa(device_index: int):
     """Pin this process to the CPU cores local to GPU ``device_index`` (``/sys/bus/pci/devices/<bdf>/local_cpulist``)
     so that pinned host buffers allocated afterwards live on the GPU's NUMA node -- with one process per GPU

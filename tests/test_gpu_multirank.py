@@ -1,6 +1,7 @@
 """Rank-level bitwise test of the multi-GPU layer on real devices (needs >= 2 GPUs in the box; skips otherwise, the
 gloo tests in test_distributed_cpu.py cover the same ownership / placement logic on the CPU): two NCCL ranks run
-``generate_gathered`` (chunk-interleaved ownership, all-gather overlapped with generation) and ``generate_sharded``;
+``generate_gathered`` (chunk-interleaved ownership, all-gather overlapped with generation), ``generate_gathered_p2p``
+(the same delivery by CUDA-IPC peer pushes with the copy engines) and ``generate_sharded``;
 every rank's result must equal a single-GPU ``generate`` of the same global realization ids bit for bit."""
 import os
 import socket
@@ -59,9 +60,13 @@ def _worker(rank, world, port, q):
     ok_shard = bool(torch.equal(part, ref[start:start + count]))
     allr, _ = D.generate_sharded(b, nreal, seed=seed, gather=True)
     ok_all = bool(torch.equal(allr, ref[:nreal]))
+    # the same delivery by peer pushes over NVLink (CUDA IPC + copy engines) instead of the NCCL collective
+    pushed = torch.zeros((padded, b.ld), dtype=torch.float64, device=b.device)
+    D.generate_gathered_p2p(b, nreal, seed=seed, chunk=24, out=pushed)
+    ok_p2p = bool(torch.equal(pushed, ref))
     dist.barrier()
     dist.destroy_process_group()
-    q.put((rank, ok_gather, ok_shard, ok_all))
+    q.put((rank, ok_gather, ok_shard, ok_all and ok_p2p))
 
 
 def test_two_ranks_equal_a_single_gpu_run_bit_for_bit():
