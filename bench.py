@@ -53,11 +53,12 @@ def peaks():
 
 
 def source_hash():
-    """sha256 over the kernel sources: stamps profile captures so a stale `traffic` figure is visible."""
+    """sha256 over the generator kernel's device code (ptar_generate.cuh, ptar_rng.cuh): stamps the ncu capture that
+    `roofline.traffic` comes from, so a figure captured from an older generator is visibly stale."""
     h = hashlib.sha256()
     d = os.path.join(ROOT, "pta_replicator_b200", "csrc")
     for f in sorted(os.listdir(d)):
-        if f.endswith((".cu", ".cuh")):
+        if f in ("ptar_generate.cuh", "ptar_rng.cuh"):      # the device code of the captured kernel (gen_kernel)
             with open(os.path.join(d, f), "rb") as fh:
                 h.update(fh.read())
     return h.hexdigest()[:16]
