@@ -236,3 +236,18 @@ def test_population_partition_matches_the_reference_function():
     d = z_to_dcom(np.array([1e-3, 0.5, 1.0]))
     mpc = 3.0856775814913674e24
     assert abs(d[0] / mpc - 1e-3 * 2.99792458e5 / 69.32) < 2e-3 and d[0] < d[1] < d[2] and 3200 < d[2] / mpc < 3500
+
+
+def test_radix256_digit_slices_of_the_tensor_core_synthesis():
+    """engine.PulsarBatch.radix256_digits (the host restatement of the digit slicing in csrc/ptar_gwb_i8.cuh): six signed
+    int8 digits reproduce round(x 2^48) exactly for |x| <= 1/4, digits stay in [-128, 127], |x| > 1/4 is refused."""
+    from pta_replicator_b200.engine import PulsarBatch
+    rng = np.random.default_rng(12)
+    x = np.r_[rng.uniform(-0.25, 0.25, 4000), 0.25, -0.25, 0.0, 2.0 ** -48, -2.0 ** -49, 127 / 256 * 0.5]
+    d = PulsarBatch.radix256_digits(x)
+    assert d.dtype == np.int8 and d.shape == (6, len(x))
+    rec = sum(d[s].astype(np.int64) * 256 ** (5 - s) for s in range(6))
+    assert np.array_equal(rec, np.rint(x * 2.0 ** 48).astype(np.int64))
+    assert np.abs(rec * 2.0 ** -48 - x).max() <= 2.0 ** -49
+    with pytest.raises(ValueError):
+        PulsarBatch.radix256_digits(np.array([0.6]))
